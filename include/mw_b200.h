@@ -1,0 +1,185 @@
+/*
+ * mw_b200.h — C ABI of the B200-native Whisper hot path (libmw_b200.so).
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference has no native code of its own;
+ * its hot path is entered from Python at
+ *     /root/reference/transcribe.py:107-113   whisperx.load_model(...)
+ *     /root/reference/transcribe.py:123       model.transcribe(audio, batch_size=..., language="zh")
+ * and the arithmetic lives in three third-party seams beneath that call, which are what these
+ * entry points replace one for one:
+ *     S1  whisperx.audio.log_mel_spectrogram(audio, n_mels, padding, device)      -> mw_logmel / mw_logmel_long
+ *     S2  ctranslate2.models.Whisper.encode(StorageView[B,n_mels,3000])            -> mw_encode
+ *     S3  ctranslate2.models.Whisper.generate(enc, prompts, beam_size, patience,   -> mw_generate
+ *             length_penalty, max_length, suppress_blank, suppress_tokens)
+ *     (+) ctranslate2.models.Whisper.detect_language(enc)  [SURVEY §8(f) rank 2]   -> mw_detect_language
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is DEVICE memory owned by the caller, h_* is host.
+ *   - every call returns mw_status (0 = ok); the message is in mw_last_error() (thread-local).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued there, no hidden sync unless stated.
+ *   - one mw_model per GPU; calls on one model must be serialised by the caller; the library
+ *     selects the model's device itself.
+ *   - no allocation on the hot path: the model owns a workspace sized at create for max_batch.
+ */
+#ifndef MW_B200_H
+#define MW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MW_ABI_VERSION 1
+
+typedef int32_t mw_status;
+enum {
+    MW_OK = 0,
+    MW_ERR_INVALID = 1,   /* bad argument */
+    MW_ERR_CUDA = 2,      /* CUDA runtime/driver error */
+    MW_ERR_UNSUPPORTED = 3,
+    MW_ERR_STATE = 4
+};
+
+int mw_abi_version(void);
+const char* mw_last_error(void);
+/* number of kernels this library has launched since load (process-wide); bench.py's gpu_launches */
+uint64_t mw_launch_count(void);
+
+/* ------------------------------------------------------------------ S1: log-mel ---------------- */
+typedef struct mw_logmel_plan mw_logmel_plan;
+
+/* h_filters: host float32 [n_mels, 201] mel filterbank (whisperx assets/mel_filters.npz layout).
+ * max_chunks bounds n_chunks of later calls. */
+mw_status mw_logmel_plan_create(int n_mels, const float* h_filters, int max_chunks, int device,
+                                mw_logmel_plan** out_plan);
+void mw_logmel_plan_destroy(mw_logmel_plan* plan);
+
+/* The pipeline's per-chunk call: chunk c = d_audio[d_offsets[c] .. +d_lengths[c]) zero-padded to
+ * 480000 samples, own global max.  d_out: float32 [n_chunks, n_mels, 3000].
+ * d_out_t (may be NULL): additionally emits the bf16 time-major copy [n_chunks, 3002, n_mels]
+ * (rows 0 and 3001 zero) that mw_encode's conv stem reads. */
+mw_status mw_logmel(mw_logmel_plan* plan, const float* d_audio, int64_t n_audio,
+                    const int64_t* d_offsets, const int32_t* d_lengths, int n_chunks,
+                    float* d_out, void* d_out_t, void* stream);
+
+/* Un-chunked log_mel_spectrogram(audio[0:n], n_mels, padding): one global max over the whole
+ * clip.  d_out: float32 [n_mels, (n+padding)/160]. */
+mw_status mw_logmel_long(mw_logmel_plan* plan, const float* d_audio, int64_t n, int64_t padding,
+                         float* d_out, void* stream);
+
+/* ------------------------------------------------------------------ model ---------------------- */
+typedef struct mw_model mw_model;
+
+typedef struct mw_model_config {
+    int32_t n_mels, d_model, n_heads, enc_layers, dec_layers, ffn, vocab;
+    int32_t n_audio_ctx;   /* 1500 */
+    int32_t n_text_ctx;    /* 448  */
+    int32_t max_batch;     /* chunks per mw_encode / mw_generate call */
+    int32_t max_beam;      /* 1 = greedy only */
+    int32_t device;
+} mw_model_config;
+
+/* Weight table: device pointers in the order of enum mw_weight_id, then per-layer blocks.
+ * Matrices are bf16 row-major [out, in] (torch Linear layout); vectors are fp32.  Pointers are
+ * BORROWED and must outlive the model.  Layouts the engine needs that differ from the checkpoint
+ * (conv taps folded into K, q|k|v concatenated, zero k-bias) are prepared by the host shim
+ * (manual_whisper_b200/engine.py: pack_weights). */
+enum mw_weight_id {
+    MW_W_CONV1 = 0,       /* bf16 [d, 3*n_mels]  k-major: [co][tap][ci] */
+    MW_B_CONV1,           /* f32  [d] */
+    MW_W_CONV2,           /* bf16 [d, 3*d]       [co][tap][ci] */
+    MW_B_CONV2,           /* f32  [d] */
+    MW_ENC_POS,           /* f32  [n_audio_ctx, d] */
+    MW_ENC_LN_G, MW_ENC_LN_B,   /* f32 [d] final encoder LayerNorm */
+    MW_DEC_EMB,           /* bf16 [vocab, d] token embedding (tied output projection) */
+    MW_DEC_POS,           /* f32  [n_text_ctx, d] */
+    MW_DEC_LN_G, MW_DEC_LN_B,   /* f32 [d] final decoder LayerNorm */
+    MW_GLOBAL_COUNT
+};
+enum mw_enc_layer_weight_id {
+    MW_EL_LN1_G = 0, MW_EL_LN1_B,
+    MW_EL_WQKV,           /* bf16 [3d, d]   q|k|v rows */
+    MW_EL_BQKV,           /* f32  [3d]      k part zero */
+    MW_EL_WO, MW_EL_BO,   /* bf16 [d, d], f32 [d] */
+    MW_EL_LN2_G, MW_EL_LN2_B,
+    MW_EL_W1, MW_EL_B1,   /* bf16 [ffn, d], f32 [ffn] */
+    MW_EL_W2, MW_EL_B2,   /* bf16 [d, ffn], f32 [d] */
+    MW_EL_COUNT
+};
+enum mw_dec_layer_weight_id {
+    MW_DL_LN1_G = 0, MW_DL_LN1_B,
+    MW_DL_WQKV, MW_DL_BQKV,
+    MW_DL_WO, MW_DL_BO,
+    MW_DL_LNX_G, MW_DL_LNX_B,   /* encoder_attn_layer_norm */
+    MW_DL_WXQ, MW_DL_BXQ,       /* cross q: bf16 [d,d], f32 [d] */
+    MW_DL_WXKV, MW_DL_BXKV,     /* cross k|v: bf16 [2d,d], f32 [2d] (k part zero) */
+    MW_DL_WXO, MW_DL_BXO,
+    MW_DL_LN2_G, MW_DL_LN2_B,
+    MW_DL_W1, MW_DL_B1,
+    MW_DL_W2, MW_DL_B2,
+    MW_DL_COUNT
+};
+typedef struct mw_weight_table {
+    int32_t n;               /* MW_GLOBAL_COUNT + enc_layers*MW_EL_COUNT + dec_layers*MW_DL_COUNT */
+    const void* const* ptrs; /* host array of device pointers */
+} mw_weight_table;
+
+mw_status mw_model_create(const mw_model_config* cfg, const mw_weight_table* weights, mw_model** out_model);
+void mw_model_destroy(mw_model* model);
+/* bytes of device workspace the model allocated at create */
+int64_t mw_model_workspace_bytes(const mw_model* model);
+
+/* S2. d_mel: float32 [B, n_mels, 3000]; d_enc_out: bf16 [B, n_audio_ctx, d_model]. */
+mw_status mw_encode(mw_model* model, const float* d_mel, int B, void* d_enc_out, void* stream);
+/* Same, reading the bf16 time-major features mw_logmel emitted ([B, 3002, n_mels]). */
+mw_status mw_encode_t(mw_model* model, const void* d_mel_t, int B, void* d_enc_out, void* stream);
+
+typedef struct mw_gen_options {
+    int32_t beam_size;            /* 1 = greedy */
+    float   patience;
+    float   length_penalty;
+    int32_t max_length;           /* 448 */
+    int32_t n_suppress;           /* ids masked at every step (already expanded, no -1) */
+    const int32_t* h_suppress;    /* host */
+    int32_t n_suppress_begin;     /* ids masked at the first generated step */
+    const int32_t* h_suppress_begin;
+    int32_t eot;
+    int32_t timestamp_begin;
+    int32_t no_timestamps;
+    int32_t with_timestamps;      /* 1 = apply the timestamp rules */
+    int32_t max_initial_timestamp_index;
+    int32_t num_hypotheses;       /* <= beam_size */
+    int32_t forced_eot_len;       /* bench-only knob: >0 forces <eot> after this many tokens; 0 = off */
+} mw_gen_options;
+
+/* S3.  d_enc: bf16 [B, n_audio_ctx, d_model].  One shared prompt (whisperx passes [prompt]*B).
+ * h_out_ids: host int32 [B, num_hypotheses, max_new] (max_new = min(max_length/2, max_length-prompt_len)),
+ * h_out_len: host int32 [B, num_hypotheses], h_out_scores: host float [B, num_hypotheses].
+ * Synchronises `stream` before returning (ids are returned to the host, like CT2). */
+mw_status mw_generate(mw_model* model, const void* d_enc, int B, const int32_t* h_prompt, int prompt_len,
+                      const mw_gen_options* opt, int32_t* h_out_ids, int32_t* h_out_len, float* h_out_scores,
+                      void* stream);
+
+/* Teacher-forced decoder logits for parity tests: tokens host int32 [B, n]; d_logits float32 [B, n, vocab]. */
+mw_status mw_decoder_logits(mw_model* model, const void* d_enc, int B, const int32_t* h_tokens, int n,
+                            float* d_logits, void* stream);
+
+/* softmax over the language ids at the <sot> position: h_probs float [B, n_langs]. */
+mw_status mw_detect_language(mw_model* model, const void* d_enc, int B, int32_t sot, int32_t first_lang,
+                             int32_t n_langs, float* h_probs, void* stream);
+
+/* ------------------------------------------------------------------ building blocks ------------
+ * Exposed so tests can pin each kernel against torch on its own (tests/test_gpu_kernels.py). */
+/* D[M,N] = A[M,K] . W[N,K]^T (+bias[N]) (gelu) (+residual f32[M,N]); A,W bf16; out bf16 or f32. */
+mw_status mw_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, const float* d_residual,
+                       void* d_out, int M, int N, int K, int gelu, int out_f32, void* stream);
+/* encoder self-attention on packed qkv bf16 [B*T, 3*d]; out bf16 [B*T, d] */
+mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream);
+mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
+                       int rows, int d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MW_B200_H */

@@ -1,0 +1,246 @@
+// Fused log-mel kernels for sm_100a — replaces whisperx.audio.log_mel_spectrogram
+// (reached from /root/reference/transcribe.py:123).
+//
+// Kernel 1 (logmel_tile_kernel): one CTA = 32 frames of one chunk.  Samples are staged once in shared
+// memory (coalesced reads, reflect/zero padding resolved on the fly), each frame is windowed and
+// transformed by an in-shared-memory 200-point complex FFT (radix 8 x 25), split to the 201 real-input
+// bins, squared, projected through the sparse mel filterbank, log10-clamped and written; the per-chunk
+// maximum is reduced CTA-wide and folded into one atomicMax per CTA.
+// Kernel 2 (logmel_finalize_kernel): max(x, chunkmax-8), (x+4)/4 in place (the tile kernel's output is
+// still L2-resident) and, optionally, the bf16 time-major copy the encoder's conv stem reads.
+#include "mw_common.cuh"
+#include "logmel_core.cuh"
+
+#include <vector>
+
+using namespace mw::logmel;
+
+namespace {
+
+struct TileSmem {
+    cpx Y[FR * 200];          // 51200 B
+    float stage[STAGE_N];     // 21440 B
+    float P[FR * PS];         // 25728 B
+    float win[N_FFT];         // 1600 B
+    cpx tw200[200];           // 1600 B
+    cpx tw400[N_FREQ + 1];    // 1616 B
+    float red[NT / 32];
+};
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned b) {
+    return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+}
+
+__global__ void __launch_bounds__(NT, 2)
+logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
+                   const int64_t* __restrict__ offsets, const int32_t* __restrict__ lengths,
+                   int64_t single_len, int64_t padded, int64_t n_frames, int n_mels,
+                   const float* __restrict__ tables,   // win[400] | tw200[200*2] | tw400[202*2]
+                   const int* __restrict__ mel_lo, const int* __restrict__ mel_cnt,
+                   const int* __restrict__ mel_off, const float* __restrict__ mel_w,
+                   float* __restrict__ out, unsigned* __restrict__ gmax) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y;
+    const int64_t frame0 = (int64_t)blockIdx.x * FR;
+
+    int64_t off = 0, len = single_len;
+    if (offsets) {
+        off = offsets[chunk];
+        len = lengths[chunk];
+        if (off < 0) off = 0;
+        if (off > n_audio) off = n_audio;
+        if (len > n_audio - off) len = n_audio - off;
+        if (len > padded) len = padded;
+        if (len < 0) len = 0;
+    }
+    // constant tables -> shared (divergent indices would serialise in the constant cache)
+    for (int i = tid; i < N_FFT; i += NT) s.win[i] = tables[i];
+    {
+        const float2* t2 = reinterpret_cast<const float2*>(tables + N_FFT);
+        for (int i = tid; i < 200; i += NT) { float2 v = t2[i]; s.tw200[i] = {v.x, v.y}; }
+        for (int i = tid; i < N_FREQ; i += NT) { float2 v = t2[200 + i]; s.tw400[i] = {v.x, v.y}; }
+    }
+    stage_load(tid, s.stage, audio + off, len, padded, frame0);
+    __syncthreads();
+    stage_radix8(tid, s.stage, s.win, s.tw200, s.Y);
+    __syncthreads();
+    stage_radix25(tid, s.Y);
+    __syncthreads();
+    stage_power(tid, s.Y, s.tw400, s.P);
+    __syncthreads();
+    float vmax = stage_mel(tid, s.P, n_mels, mel_lo, mel_cnt, mel_off, mel_w,
+                           out + (int64_t)chunk * n_mels * n_frames, n_frames, frame0, n_frames, -INFINITY);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((tid & 31) == 0) s.red[tid >> 5] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = s.red[0];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, s.red[w]);
+        atomicMax(gmax + chunk, ordered_bits(m));
+    }
+}
+
+// grid: (ceil(n_frames/32), n_chunks); block 256 (8 warps, warp w handles mels w, w+8, ...)
+__global__ void __launch_bounds__(256)
+logmel_finalize_kernel(float* __restrict__ out, const unsigned* __restrict__ gmax, int n_mels, int64_t n_frames,
+                       __nv_bfloat16* __restrict__ out_t /* [chunks, n_frames+2, n_mels] or null */) {
+    __shared__ float tile[128][33];
+    const int chunk = blockIdx.y;
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float g = from_ordered_bits(gmax[chunk]);
+    float* o = out + (int64_t)chunk * n_mels * n_frames;
+    const bool valid = f0 + lane < n_frames;
+    for (int m0 = 0; m0 < n_mels; m0 += 128) {
+        for (int m = m0 + warp; m < min(n_mels, m0 + 128); m += 8) {
+            float v = 0.0f;
+            if (valid) {
+                v = finalize_value(o[(int64_t)m * n_frames + f0 + lane], g);
+                o[(int64_t)m * n_frames + f0 + lane] = v;
+            }
+            tile[m - m0][lane] = v;
+        }
+        if (out_t) {
+            __syncthreads();
+            __nv_bfloat16* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
+            const int mcount = min(128, n_mels - m0);
+            // 32 frames x mcount mels, mel fastest
+            for (int i = threadIdx.x; i < 32 * mcount; i += 256) {
+                const int f = i / mcount, m = i - f * mcount;
+                if (f0 + f < n_frames) ot[(f0 + f + 1) * n_mels + m0 + m] = __float2bfloat16(tile[m][f]);
+            }
+            __syncthreads();
+        }
+    }
+    if (out_t && blockIdx.x == 0) {
+        __nv_bfloat16* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
+        for (int i = threadIdx.x; i < n_mels; i += 256) {
+            ot[i] = __float2bfloat16(0.0f);
+            ot[(n_frames + 1) * n_mels + i] = __float2bfloat16(0.0f);
+        }
+    }
+}
+
+}  // namespace
+
+struct mw_logmel_plan {
+    int device = 0;
+    int n_mels = 0;
+    int max_chunks = 0;
+    float* d_tables = nullptr;
+    int* d_lo = nullptr;
+    int* d_cnt = nullptr;
+    int* d_off = nullptr;
+    float* d_w = nullptr;
+    unsigned* d_gmax = nullptr;
+};
+
+extern "C" mw_status mw_logmel_plan_create(int n_mels, const float* h_filters, int max_chunks, int device,
+                                           mw_logmel_plan** out_plan) {
+    MW_REQUIRE(out_plan && h_filters, "mw_logmel_plan_create: null argument");
+    MW_REQUIRE(n_mels > 0 && n_mels <= 1024, "mw_logmel_plan_create: n_mels=%d out of range", n_mels);
+    MW_REQUIRE(max_chunks > 0 && max_chunks <= 65535, "mw_logmel_plan_create: max_chunks=%d out of range (1..65535)", max_chunks);
+    mw::DeviceGuard guard(device);
+    auto* p = new mw_logmel_plan();
+    p->device = device;
+    p->n_mels = n_mels;
+    p->max_chunks = max_chunks;
+    // twiddle / window tables in double, rounded once
+    std::vector<float> tab(N_FFT + 2 * 200 + 2 * (N_FREQ + 1), 0.0f);
+    const double PI = 3.14159265358979323846;
+    for (int n = 0; n < N_FFT; ++n) tab[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / N_FFT));
+    for (int m = 0; m < 200; ++m) {
+        tab[N_FFT + 2 * m] = (float)cos(2.0 * PI * m / 200.0);
+        tab[N_FFT + 2 * m + 1] = (float)(-sin(2.0 * PI * m / 200.0));
+    }
+    for (int k = 0; k <= 200; ++k) {
+        tab[N_FFT + 400 + 2 * k] = (float)cos(2.0 * PI * k / 400.0);
+        tab[N_FFT + 400 + 2 * k + 1] = (float)(-sin(2.0 * PI * k / 400.0));
+    }
+    // sparse filter rows: [first nonzero, last nonzero]
+    std::vector<int> lo(n_mels), cnt(n_mels), off(n_mels);
+    std::vector<float> w;
+    for (int m = 0; m < n_mels; ++m) {
+        int a = N_FREQ, b = -1;
+        for (int k = 0; k < N_FREQ; ++k)
+            if (h_filters[m * N_FREQ + k] != 0.0f) { if (k < a) a = k; b = k; }
+        lo[m] = (b >= 0) ? a : 0;
+        cnt[m] = (b >= 0) ? (b - a + 1) : 0;
+        off[m] = (int)w.size();
+        for (int k = 0; k < cnt[m]; ++k) w.push_back(h_filters[m * N_FREQ + lo[m] + k]);
+    }
+    if (w.empty()) w.push_back(0.0f);
+    MW_CUDA_CHECK(cudaMalloc(&p->d_tables, tab.size() * sizeof(float)));
+    MW_CUDA_CHECK(cudaMalloc(&p->d_lo, n_mels * sizeof(int)));
+    MW_CUDA_CHECK(cudaMalloc(&p->d_cnt, n_mels * sizeof(int)));
+    MW_CUDA_CHECK(cudaMalloc(&p->d_off, n_mels * sizeof(int)));
+    MW_CUDA_CHECK(cudaMalloc(&p->d_w, w.size() * sizeof(float)));
+    MW_CUDA_CHECK(cudaMalloc(&p->d_gmax, max_chunks * sizeof(unsigned)));
+    MW_CUDA_CHECK(cudaMemcpy(p->d_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    MW_CUDA_CHECK(cudaMemcpy(p->d_lo, lo.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    MW_CUDA_CHECK(cudaMemcpy(p->d_cnt, cnt.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    MW_CUDA_CHECK(cudaMemcpy(p->d_off, off.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    MW_CUDA_CHECK(cudaMemcpy(p->d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    MW_CUDA_CHECK(cudaFuncSetAttribute(logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TileSmem)));
+    *out_plan = p;
+    return MW_OK;
+}
+
+extern "C" void mw_logmel_plan_destroy(mw_logmel_plan* p) {
+    if (!p) return;
+    mw::DeviceGuard guard(p->device);
+    cudaFree(p->d_tables); cudaFree(p->d_lo); cudaFree(p->d_cnt); cudaFree(p->d_off);
+    cudaFree(p->d_w); cudaFree(p->d_gmax);
+    delete p;
+}
+
+static mw_status run_logmel(mw_logmel_plan* p, const float* d_audio, int64_t n_audio, const int64_t* d_offsets,
+                            const int32_t* d_lengths, int n_chunks, int64_t single_len, int64_t padded,
+                            float* d_out, void* d_out_t, cudaStream_t st) {
+    const int64_t n_frames = padded / HOP;
+    if (n_frames == 0 || n_chunks == 0) return MW_OK;
+    const int64_t tiles = mw::ceil_div64(n_frames, FR);
+    MW_REQUIRE(tiles <= 2147483647LL, "mw_logmel: clip too long");
+    mw::DeviceGuard guard(p->device);
+    MW_CUDA_CHECK(cudaMemsetAsync(p->d_gmax, 0, n_chunks * sizeof(unsigned), st));
+    dim3 grid((unsigned)tiles, (unsigned)n_chunks);
+    logmel_tile_kernel<<<grid, NT, sizeof(TileSmem), st>>>(d_audio, n_audio, d_offsets, d_lengths, single_len, padded,
+                                                          n_frames, p->n_mels, p->d_tables, p->d_lo, p->d_cnt,
+                                                          p->d_off, p->d_w, d_out, p->d_gmax);
+    MW_LAUNCH_CHECK();
+    logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (__nv_bfloat16*)d_out_t);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+extern "C" mw_status mw_logmel(mw_logmel_plan* plan, const float* d_audio, int64_t n_audio, const int64_t* d_offsets,
+                               const int32_t* d_lengths, int n_chunks, float* d_out, void* d_out_t, void* stream) {
+    MW_REQUIRE(plan, "mw_logmel: null plan");
+    MW_REQUIRE(n_chunks >= 0 && n_chunks <= plan->max_chunks, "mw_logmel: n_chunks=%d exceeds plan max_chunks=%d",
+               n_chunks, plan->max_chunks);
+    if (n_chunks == 0) return MW_OK;
+    MW_REQUIRE(d_audio && d_offsets && d_lengths && d_out, "mw_logmel: null device pointer");
+    return run_logmel(plan, d_audio, n_audio, d_offsets, d_lengths, n_chunks, 0, 480000, d_out, d_out_t,
+                      (cudaStream_t)stream);
+}
+
+extern "C" mw_status mw_logmel_long(mw_logmel_plan* plan, const float* d_audio, int64_t n, int64_t padding,
+                                    float* d_out, void* stream) {
+    MW_REQUIRE(plan, "mw_logmel_long: null plan");
+    MW_REQUIRE(n >= 0 && padding >= 0, "mw_logmel_long: negative length");
+    // torch.stft(center=True, pad_mode='reflect') needs more than n_fft/2 samples
+    MW_REQUIRE(n + padding > N_FFT / 2, "mw_logmel_long: input of %lld samples is too short for reflect padding of %d",
+               (long long)(n + padding), N_FFT / 2);
+    MW_REQUIRE(d_audio || n == 0, "mw_logmel_long: null audio");
+    MW_REQUIRE(d_out, "mw_logmel_long: null output");
+    return run_logmel(plan, d_audio, n, nullptr, nullptr, 1, n, n + padding, d_out, nullptr, (cudaStream_t)stream);
+}

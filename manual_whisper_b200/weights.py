@@ -1,0 +1,102 @@
+"""Seeded random-init Whisper weights with Hugging Face key names.
+
+There is no network, so no checkpoint exists on disk; the reference loads
+real weights through ``whisperx.load_model`` (/root/reference/transcribe.py:107-113).  Parity runs
+use a seeded random-init state dict whose values are rounded to bf16 ONCE; the very same rounded
+values go to the oracle (as fp32) and to the CUDA engine (as bf16), SURVEY.md §8(d).
+
+Key names follow ``transformers`` ``WhisperForConditionalGeneration.state_dict()`` so a real
+checkpoint can be fed through the same door later.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+from .config import ModelDims
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    """Encoder positional table: cat(sin, cos) with log-spaced timescales."""
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2, dtype=torch.float32))
+    t = torch.arange(length, dtype=torch.float32)[:, None] * inv[None, :]
+    return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+def _keys(dims: ModelDims):
+    d, f = dims.d_model, dims.ffn
+    yield "model.encoder.conv1.weight", (d, dims.n_mels, 3), "w"
+    yield "model.encoder.conv1.bias", (d,), "b"
+    yield "model.encoder.conv2.weight", (d, d, 3), "w"
+    yield "model.encoder.conv2.bias", (d,), "b"
+    for side, n_layers in (("encoder", dims.enc_layers), ("decoder", dims.dec_layers)):
+        for i in range(n_layers):
+            p = f"model.{side}.layers.{i}."
+            attns = ["self_attn"] + (["encoder_attn"] if side == "decoder" else [])
+            for a in attns:
+                for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                    yield p + f"{a}.{proj}.weight", (d, d), "w"
+                    if proj != "k_proj":
+                        yield p + f"{a}.{proj}.bias", (d,), "b"
+                yield p + f"{a}_layer_norm.weight", (d,), "g"
+                yield p + f"{a}_layer_norm.bias", (d,), "beta"
+            yield p + "fc1.weight", (f, d), "w"
+            yield p + "fc1.bias", (f,), "b"
+            yield p + "fc2.weight", (d, f), "w"
+            yield p + "fc2.bias", (d,), "b"
+            yield p + "final_layer_norm.weight", (d,), "g"
+            yield p + "final_layer_norm.bias", (d,), "beta"
+        yield f"model.{side}.layer_norm.weight", (d,), "g"
+        yield f"model.{side}.layer_norm.bias", (d,), "beta"
+    yield "model.decoder.embed_tokens.weight", (dims.vocab, d), "emb"
+    yield "model.decoder.embed_positions.weight", (dims.n_text_ctx, d), "pos"
+
+
+def random_init(dims: ModelDims, seed: int = 1234, scheme: str = "survey") -> Dict[str, torch.Tensor]:
+    """Seeded weights, fp32 tensors holding bf16-representable values.
+
+    scheme "survey": N(0, 0.02^2) matrices/embeddings/biases, LayerNorm gamma=1 beta=0.
+    scheme "lively": fan-in scaled matrices (std = gain/sqrt(fan_in)), wider embeddings, randomised
+    LayerNorm affine and biases, so attention is not uniform and the decoded ids depend on the
+    audio; documented in DESIGN.md and used identically by the oracle and the engine.
+    """
+    if scheme not in ("survey", "lively"):
+        raise ValueError("scheme must be 'survey' or 'lively'")
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, kind in _keys(dims):
+        if kind == "g":
+            t = torch.ones(shape)
+            if scheme == "lively":
+                t = t + 0.1 * torch.randn(shape, generator=g)
+        elif kind == "beta":
+            t = torch.zeros(shape)
+            if scheme == "lively":
+                t = 0.1 * torch.randn(shape, generator=g)
+        else:
+            t = torch.randn(shape, generator=g)
+            if scheme == "survey":
+                t = t * 0.02
+            elif kind == "w":
+                fan_in = shape[1] * (shape[2] if len(shape) == 3 else 1)
+                gain = 2.0 if ("q_proj" in name or "k_proj" in name) else 1.0
+                t = t * (gain / math.sqrt(fan_in))
+            elif kind == "b":
+                t = t * 0.1
+            elif kind == "emb":
+                t = t * 0.05
+            else:
+                t = t * 0.1
+        sd[name] = t.to(torch.bfloat16).to(torch.float32)
+    sd["model.encoder.embed_positions.weight"] = sinusoids(dims.n_audio_ctx, dims.d_model)
+    return sd
+
+
+def to_hf(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out = dict(sd)
+    out["proj_out.weight"] = sd["model.decoder.embed_tokens.weight"]
+    return out
