@@ -13,7 +13,5 @@ extern "C" mw_status mw_generate(mw_model*, const void*, int, const int32_t*, in
                                  int32_t*, float*, void*) { MW_STUB(mw_generate); }
 extern "C" mw_status mw_decoder_logits(mw_model*, const void*, int, const int32_t*, int, float*, void*) { MW_STUB(mw_decoder_logits); }
 extern "C" mw_status mw_detect_language(mw_model*, const void*, int, int32_t, int32_t, int32_t, float*, void*) { MW_STUB(mw_detect_language); }
-extern "C" mw_status mw_gemm_bf16(const void*, const void*, const float*, const float*, void*, int, int, int, int, int,
-                                  void*) { MW_STUB(mw_gemm_bf16); }
 extern "C" mw_status mw_attention_bf16(const void*, void*, int, int, int, void*) { MW_STUB(mw_attention_bf16); }
 extern "C" mw_status mw_layernorm(const float*, const float*, const float*, void*, int, int, void*) { MW_STUB(mw_layernorm); }
