@@ -1,0 +1,111 @@
+// Small bandwidth-bound kernels around the tensor-core work: LayerNorm (fp32 residual stream -> bf16 GEMM
+// operand) and the feature re-layout mw_encode needs (f32 [B, n_mels, frames] -> bf16 time-major).
+#include "mw_common.cuh"
+#include "kernels.cuh"
+
+namespace mw {
+
+namespace {
+
+// one warp per row; d % 128 == 0, d <= 128 * MAXV
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ out, int rows, int d) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * d);
+    const int nv = d >> 7;   // float4 per lane
+    float4 v[MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = xr[i * 32 + lane];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)d + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    uint2* o2 = reinterpret_cast<uint2*>(out + (int64_t)row * d);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const float4 g = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            o2[i * 32 + lane] = u;
+        }
+}
+
+// f32 [B, C, F] -> bf16 [B, F+2, C] with zero rows 0 and F+1
+__global__ void __launch_bounds__(256)
+features_to_time_major_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int F) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float* src = in + (int64_t)b * C * F;
+    __nv_bfloat16* dst = out + (int64_t)b * (F + 2) * C;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, f = f0 + tx;
+        tile[i][tx] = (c < C && f < F) ? src[(int64_t)c * F + f] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int f = f0 + i, c = c0 + tx;
+        if (f < F && c < C) dst[(int64_t)(f + 1) * C + c] = __float2bfloat16(tile[tx][i]);
+    }
+    if (blockIdx.x == 0 && ty == 0) {
+        const int c = c0 + tx;
+        if (c < C) {
+            dst[c] = __float2bfloat16(0.0f);
+            dst[(int64_t)(F + 1) * C + c] = __float2bfloat16(0.0f);
+        }
+    }
+}
+
+}  // namespace
+
+mw_status layernorm_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int d,
+                           cudaStream_t st) {
+    MW_REQUIRE(x && gamma && beta && out_bf16, "layernorm: null pointer");
+    MW_REQUIRE(d % 128 == 0 && d >= 128 && d <= 2048, "layernorm: d=%d must be a multiple of 128 in [128, 2048]", d);
+    if (rows <= 0) return MW_OK;
+    const int grid = ceil_div(rows, 8);
+    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
+    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
+    else layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+mw_status features_to_time_major_launch(const float* in, void* out_bf16, int B, int C, int F, cudaStream_t st) {
+    dim3 grid(ceil_div(F, 32), ceil_div(C, 32), B);
+    features_to_time_major_kernel<<<grid, 256, 0, st>>>(in, (__nv_bfloat16*)out_bf16, C, F);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+}  // namespace mw
+
+extern "C" mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
+                                  int rows, int d, void* stream) {
+    return mw::layernorm_launch(d_x, d_gamma, d_beta, d_out_bf16, rows, d, (cudaStream_t)stream);
+}
