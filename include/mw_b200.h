@@ -179,6 +179,11 @@ mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_
 mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
                        int rows, int d, void* stream);
 
+/* Measurement hook for bench.py's roofline: average duration (ms, CUDA events on `stream`) of one hot decode
+ * kernel launched `iters` times back to back over different layers' data (inputs larger than L2).
+ * which: 0 = cross-attention decode, 1 = skinny GEMM (fc1 weights), 2 = skinny GEMM (out-proj weights). */
+mw_status mw_bench_kernel(mw_model* model, int which, int B, int iters, float* h_ms_avg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1152,3 +1152,47 @@ extern "C" mw_status mw_detect_language(mw_model* m, const void* d_enc, int B, i
     }
     return MW_OK;
 }
+
+// ---- measurement hook (bench.py "roofline"): times one hot decode kernel in isolation with CUDA events on the
+// caller's stream, cycling through the layers so consecutive launches never re-read L2-resident data.
+//   which = 0 : cross-attention decode kernel, R = B rows        (bytes/launch = B*T*2d*2)
+//   which = 1 : skinny GEMM on the fc1 weights, R = B rows       (bytes/launch = ffn*d*2)
+//   which = 2 : skinny GEMM on the self-attention out-proj       (bytes/launch = d*d*2)
+extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, float* h_ms_avg, void* stream) {
+    MW_REQUIRE(m && h_ms_avg && iters > 0, "mw_bench_kernel: bad argument");
+    const mw_model_config& c = m->cfg;
+    DecoderState* s = m->dec;
+    MW_REQUIRE(B > 0 && B <= c.max_batch, "mw_bench_kernel: B outside 1..max_batch");
+    mw::DeviceGuard guard(c.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = c.d_model, T = c.n_audio_ctx;
+    cudaEvent_t e0, e1;
+    MW_CUDA_CHECK(cudaEventCreate(&e0));
+    MW_CUDA_CHECK(cudaEventCreate(&e1));
+    auto one = [&](int l) -> mw_status {
+        if (which == 0) {
+            __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
+            dim3 grid(c.n_heads, B);
+            decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(s->qx, d, kv, kv + d, 2 * d, T, nullptr, c.n_text_ctx,
+                                                                           s->ctl, T, 1, nullptr, nullptr, 0, s->att, d);
+            MW_LAUNCH_CHECK();
+            return MW_OK;
+        }
+        if (which == 1)
+            return skinny_gemm(s->ln, d, m->dlw(l, MW_DL_W1), d, (const float*)m->dlw(l, MW_DL_B1), nullptr, s->mlp, c.ffn, B,
+                               c.ffn, d, SK_FLAG_GELU, st);
+        return skinny_gemm(s->att, d, m->dlw(l, MW_DL_WO), d, (const float*)m->dlw(l, MW_DL_BO), nullptr, s->qx, d, B, d, d, 0, st);
+    };
+    mw_status r;
+    for (int i = 0; i < 3; ++i) if ((r = one(i % c.dec_layers)) != MW_OK) return r;
+    MW_CUDA_CHECK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) if ((r = one(i % c.dec_layers)) != MW_OK) return r;
+    MW_CUDA_CHECK(cudaEventRecord(e1, st));
+    MW_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MW_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *h_ms_avg = ms / iters;
+    return MW_OK;
+}

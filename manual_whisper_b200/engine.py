@@ -195,6 +195,13 @@ class Engine:
                                               out.data_ptr(), self._stream()), "mw_decoder_logits")
         return out
 
+    def bench_kernel(self, which: int, B: int, iters: int = 64) -> float:
+        """Average ms per launch of one hot decode kernel (include/mw_b200.h: mw_bench_kernel)."""
+        ms = C.c_float(0.0)
+        _lib.check(self.lib.mw_bench_kernel(self.handle, int(which), int(B), int(iters), C.byref(ms), self._stream()),
+                   "mw_bench_kernel")
+        return float(ms.value)
+
     def detect_language(self, enc: torch.Tensor, tokens: SpecialTokens) -> np.ndarray:
         B = enc.shape[0]
         probs = np.zeros((B, tokens.n_langs), dtype=np.float32)
