@@ -201,7 +201,16 @@ class FasterWhisperPipeline:
         vad_segments = merge_chunks(vad_segments, chunk_size, onset=self._vad_params["vad_onset"],
                                     offset=self._vad_params["vad_offset"])
 
-        # ---- tokenizer (language given => no detection; rebuilt only when task/language differ)
+        language, task = self._prepare_tokenizer(audio, language, task)
+        segments = self.transcribe_windows_host(audio, vad_segments, batch_size=batch_size, language=language, task=task,
+                                                print_progress=print_progress, combined_progress=combined_progress,
+                                                verbose=verbose, _forced_eot_len=_forced_eot_len)
+        if self.preset_language is None:
+            self.tokenizer = None
+        return {"segments": segments, "language": language}
+
+    def _prepare_tokenizer(self, audio, language, task):
+        """language given => no detection; the tokenizer is rebuilt only when task/language differ."""
         if self.tokenizer is None:
             language = language or self.detect_language(audio)
             task = task or "transcribe"
@@ -211,7 +220,17 @@ class FasterWhisperPipeline:
             task = task or self.tokenizer.task_name
             if task != self.tokenizer.task_name or language != self.tokenizer.language_code:
                 self.tokenizer = Tokenizer(self.model.tokens, self.model.is_multilingual, task=task, language=language)
+        return language, task
 
+    def transcribe_windows_host(self, audio: np.ndarray, vad_segments: List[Dict], batch_size: Optional[int] = None,
+                                language: Optional[str] = None, task: Optional[str] = None, print_progress: bool = False,
+                                combined_progress: bool = False, verbose: bool = False, chunk_size: int = 30,
+                                _forced_eot_len: int = 0) -> List[Dict]:
+        """The batched loop of ``transcribe`` over an explicit window list (what a rank of the sharded
+        multi-process path runs on its share, manual_whisper_b200/distributed.py)."""
+        if self.tokenizer is None or (language and language != self.tokenizer.language_code) or \
+                (task and task != self.tokenizer.task_name):
+            self._prepare_tokenizer(audio, language, task)
         options = self.options
         if self.suppress_numerals and self.tokenizer.hf is not None:
             previous = list(options.suppress_tokens or [])
@@ -239,9 +258,7 @@ class FasterWhisperPipeline:
                     print(f"Transcript: [{round(vad_segments[idx]['start'], 3)} --> {round(vad_segments[idx]['end'], 3)}] {text}")
                 segments.append({"text": text, "start": round(vad_segments[idx]["start"], 3),
                                  "end": round(vad_segments[idx]["end"], 3), "tokens": toks})
-        if self.preset_language is None:
-            self.tokenizer = None
-        return {"segments": segments, "language": language}
+        return segments
 
     # ---- batched execution over one or more replicas
     def _run_batches(self, audio, offs, lens, batch_size, options, print_progress, combined_progress, forced_eot_len):

@@ -48,7 +48,7 @@ def load_audio(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
             if w.getnchannels() > 1:
                 pcm = pcm.reshape(-1, w.getnchannels()).astype(np.int32).sum(axis=1) // w.getnchannels()
             return pcm.astype(np.float32) / 32768.0
-    except (wave.Error, EOFError) as e:
+    except (wave.Error, EOFError, OSError) as e:
         raise RuntimeError(f"Failed to load audio: {e} (ffmpeg is not installed)") from e
 
 

@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing: one process per GPU, windows sharded by batch, host gather (no data-path collective).
+
+VAD windows are independent units (same fixed prompt, no cross-window state: SURVEY.md §8e), so the N>1 path
+is: every rank computes the same window list, takes the batches ``rank, rank+world, ...``, transcribes them on
+its own GPU, and the (index, result) pairs are gathered and restored to window order.  torch.distributed is
+used only for that final object gather (NCCL or gloo — identical code path, which is what the CPU tests run).
+"""
+from __future__ import annotations
+
+from typing import Any, List, Sequence, Tuple
+
+
+def shard_batches(n_windows: int, batch_size: int, world: int, rank: int) -> List[Tuple[int, int]]:
+    """[start, end) window ranges owned by `rank`: batches dealt round-robin so every rank gets full batches first."""
+    if batch_size <= 0 or world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad sharding arguments")
+    batches = [(i, min(i + batch_size, n_windows)) for i in range(0, n_windows, batch_size)]
+    return batches[rank::world]
+
+
+def gather_ordered(local: Sequence[Tuple[int, Any]], n_windows: int, group=None) -> List[Any]:
+    """All ranks contribute (window_index, result) pairs; every rank gets the full list in window order."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        merged = list(local)
+    else:
+        bucket = [None] * dist.get_world_size(group)
+        dist.all_gather_object(bucket, list(local), group=group)
+        merged = [p for part in bucket for p in part]
+    out: List[Any] = [None] * n_windows
+    for idx, res in merged:
+        if out[idx] is not None:
+            raise RuntimeError(f"window {idx} was produced by two ranks")
+        out[idx] = res
+    missing = [i for i, r in enumerate(out) if r is None]
+    if missing:
+        raise RuntimeError(f"windows {missing[:8]} were not produced by any rank")
+    return out
+
+
+def transcribe_sharded(pipeline, audio, batch_size: int, rank: int, world: int, group=None, **kwargs):
+    """model.transcribe across `world` single-GPU processes: same return value on every rank."""
+    import numpy as np
+    from .vad import merge_chunks
+    from .config import SAMPLE_RATE
+    import torch
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    turns = pipeline.vad_model({"waveform": torch.from_numpy(audio).unsqueeze(0), "sample_rate": SAMPLE_RATE})
+    windows = merge_chunks(turns, kwargs.get("chunk_size", 30), onset=pipeline._vad_params["vad_onset"],
+                           offset=pipeline._vad_params["vad_offset"])
+    mine = shard_batches(len(windows), batch_size, world, rank)
+    local = []
+    for a, b in mine:
+        res = pipeline.transcribe_windows_host(audio, windows[a:b], batch_size=batch_size, **kwargs)
+        for k, seg in enumerate(res):
+            local.append((a + k, seg))
+    segs = gather_ordered(local, len(windows), group)
+    return {"segments": segs, "language": kwargs.get("language") or pipeline.preset_language}

@@ -1,0 +1,99 @@
+"""The public call surface on the GPU: load_model(...).transcribe(audio, batch_size) against the oracle pipeline."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import manual_whisper_b200 as mw
+    from manual_whisper_b200.config import custom_dims, scaled_tokens
+    from manual_whisper_b200.weights import random_init
+    dims = custom_dims("pipe-small", 80, 128, 2, 2, 2, 512, 2048, n_audio_ctx=1500, n_text_ctx=24)
+    tok = scaled_tokens(2048)
+    sd = random_init(dims, seed=5, scheme="lively")
+    audio, turns = mw.synthetic_speech(200.0, seed=2)
+    pipe = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+                         vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4)
+    return mw, dims, tok, sd, audio, turns, pipe
+
+
+def test_transcribe_structure_order_and_batch_tail(setup):
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    wins = mw.merge_chunks(turns, 30)
+    assert len(wins) % 4 != 0 or len(wins) > 4
+    r4 = pipe.transcribe(audio, batch_size=4, language="en")
+    r3 = pipe.transcribe(audio, batch_size=3)
+    r1 = pipe.transcribe(audio)                       # batch_size None -> 1
+    assert r4["language"] == "en" and len(r4["segments"]) == len(wins)
+    for seg, w in zip(r4["segments"], wins):
+        assert set(seg) >= {"text", "start", "end"} and seg["start"] == round(w["start"], 3) and seg["end"] == round(w["end"], 3)
+        assert isinstance(seg["text"], str) and len(seg["tokens"]) <= 12
+    # batching must not change a window's ids (per-chunk max, no cross-chunk state)
+    assert [s["tokens"] for s in r4["segments"]] == [s["tokens"] for s in r3["segments"]] == [s["tokens"] for s in r1["segments"]]
+
+
+def test_transcribe_matches_oracle_pipeline(setup):
+    from oracle.logmel import log_mel_chunks
+    from oracle.model import OracleWhisper
+    from oracle.generate import generate, GenOptions
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    res = pipe.transcribe(audio, batch_size=4)
+    wins = mw.merge_chunks(turns, 30)
+    offs = [int(w["start"] * 16000) for w in wins]
+    lens = [int(w["end"] * 16000) - o for w, o in zip(wins, offs)]
+    emu = OracleWhisper(dims, sd, emulate_bf16=True)
+    prompt = [tok.sot, tok.lang_id("en"), tok.transcribe, tok.no_timestamps]
+    same = 0
+    with torch.no_grad():
+        mel = log_mel_chunks(audio, offs, lens, 80)
+        ref, trace = generate(emu, emu.encode(mel), prompt, tok, GenOptions(beam_size=1, max_length=dims.n_text_ctx), return_trace=True)
+    for b, (seg, r) in enumerate(zip(res["segments"], ref)):
+        a, c = seg["tokens"], r.sequences_ids[0]
+        if a == c:
+            same += 1
+            continue
+        k = next(i for i in range(min(len(a), len(c))) if a[i] != c[i])
+        top = trace[k][b].topk(2).values
+        print(f"window {b} diverges at step {k}, oracle top-2 margin {(top[0] - top[1]).item():.4f}")
+        assert (top[0] - top[1]).item() < 0.05
+    print(f"identical windows: {same}/{len(ref)}")
+    assert same >= 0.7 * len(ref)
+
+
+def test_empty_vad_and_short_audio(setup, capsys):
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    saved = pipe.vad_model
+    try:
+        pipe.vad_model = mw.InjectedVad([])
+        out = pipe.transcribe(audio[:16000], batch_size=4)
+        assert out == {"segments": [], "language": "en"}
+        assert "No active speech found in audio" in capsys.readouterr().out
+        pipe.vad_model = mw.InjectedVad([(0.0, 0.5)])
+        out = pipe.transcribe(audio[:8000], batch_size=4)
+        assert len(out["segments"]) == 1 and out["segments"][0]["end"] == 0.5
+        pipe.vad_model = mw.InjectedVad([(0.0, 31.0)])
+        with pytest.raises(ValueError, match="longer than 30 s"):
+            pipe.transcribe(audio, batch_size=4)
+    finally:
+        pipe.vad_model = saved
+
+
+def test_default_energy_vad_and_language_detection(setup):
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    with pytest.warns(UserWarning):
+        p2 = mw.load_model("tiny", "cuda", compute_type="float16", asr_options={"beam_size": 1}, model=sd, dims=dims,
+                           tokens=tok, max_batch=4, vad_options={"vad_onset": 0.5, "vad_offset": 0.363})
+    out = p2.transcribe(audio[: 16000 * 60], batch_size=4)
+    assert out["language"] in mw.config.LANGUAGES[: tok.n_langs] and len(out["segments"]) >= 1
+    assert p2.tokenizer is None                      # created with language=None -> reset after the call
+
+
+def test_sharded_helper_single_process(setup):
+    from manual_whisper_b200.distributed import transcribe_sharded
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    full = pipe.transcribe(audio, batch_size=4)
+    sh = transcribe_sharded(pipe, audio, 4, rank=0, world=1, language="en")
+    assert [s["tokens"] for s in sh["segments"]] == [s["tokens"] for s in full["segments"]]
