@@ -183,6 +183,9 @@ mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_be
  * kernel launched `iters` times back to back over different layers' data (inputs larger than L2).
  * which: 0 = cross-attention decode, 1 = skinny GEMM (fc1 weights), 2 = skinny GEMM (out-proj weights). */
 mw_status mw_bench_kernel(mw_model* model, int which, int B, int iters, float* h_ms_avg, void* stream);
+/* Average ms of one decode step (CUDA-graph replay, B rows, position 0) restricted to the kernel classes in `parts`:
+ * 1 embed, 2 LayerNorm, 4 skinny GEMMs, 8 self-attention, 16 cross-attention, 32 final LN + logits GEMM. */
+mw_status mw_bench_step(mw_model* model, int B, int parts, int iters, float* h_ms_avg, void* stream);
 
 #ifdef __cplusplus
 }

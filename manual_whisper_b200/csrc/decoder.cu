@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace mw {
 
@@ -165,8 +166,97 @@ skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bflo
     }
 }
 
+// Main version: a CTA owns 16 weight rows and the whole K; its NW warps split K into contiguous runs of KB
+// 32-element blocks and issue EVERY weight load (ld.global.nc, L1 no-allocate) before touching
+// anything else, so a kernel's whole matrix is in flight at once.
+template <int KB, int NW>
+__global__ void __launch_bounds__(NW * 32)
+skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+                          const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
+                          int flags) {
+    __shared__ float red[NW][32][17];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int n0 = blockIdx.x * 16, r0 = blockIdx.y * 32;
+    const int k_start = warp * (KB * 32) + q * 8;
+    const __nv_bfloat16* wa = W + (int64_t)min(n0 + g, N - 1) * ldw + k_start;
+    const __nv_bfloat16* wb = W + (int64_t)min(n0 + g + 8, N - 1) * ldw + k_start;
+    uint4 alo[KB], ahi[KB];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+        alo[i] = ldg_stream(wa + i * 32);
+        ahi[i] = ldg_stream(wb + i * 32);
+    }
+    const __nv_bfloat16* xr[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xr[t] = X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + k_start;
+    float c[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[t][i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+        uint4 b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(xr[t] + i * 32));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            mma_bf16_16816(c[t], alo[i].x, ahi[i].x, alo[i].y, ahi[i].y, b[t].x, b[t].y);
+            mma_bf16_16816(c[t], alo[i].z, ahi[i].z, alo[i].w, ahi[i].w, b[t].z, b[t].w);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        red[warp][t * 8 + 2 * q][g] = c[t][0];
+        red[warp][t * 8 + 2 * q + 1][g] = c[t][1];
+        red[warp][t * 8 + 2 * q][g + 8] = c[t][2];
+        red[warp][t * 8 + 2 * q + 1][g + 8] = c[t][3];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 512; o += NW * 32) {
+        const int rl = o >> 4, nl = o & 15;
+        const int r = r0 + rl, n = n0 + nl;
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += red[w][rl][nl];
+        if (r < R && n < N) {
+            if (bias) v += __ldg(bias + n);
+            if (flags & SK_FLAG_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+            const int64_t oi = (int64_t)r * ldo + n;
+            if (resid) v += resid[oi];
+            if (flags & SK_FLAG_F32) reinterpret_cast<float*>(out)[oi] = v;
+            else reinterpret_cast<__nv_bfloat16*>(out)[oi] = __float2bfloat16(v);
+        }
+    }
+}
+
+template <int KB, int NW>
+mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
+                        int ldo, int R, int N, int K, int flags, cudaStream_t st) {
+    dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
+    skinny_gemm_rows16_kernel<KB, NW><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias,
+                                                                resid, out, ldo, R, N, K, flags);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
 mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
                       int ldo, int R, int N, int K, int flags, cudaStream_t st) {
+#define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st)
+    MW_SK(5, 8);    // 1280  (large)
+    MW_SK(10, 16);  // 5120  (large ffn)
+    MW_SK(4, 8);    // 1024  (medium)
+    MW_SK(8, 16);   // 4096  (medium ffn)
+    MW_SK(3, 8);    // 768   (small)
+    MW_SK(6, 16);   // 3072  (small ffn)
+    MW_SK(2, 8);    // 512   (base / test ffn)
+    MW_SK(4, 16);   // 2048  (base ffn)
+    MW_SK(3, 4);    // 384   (tiny)
+    MW_SK(6, 8);    // 1536  (tiny ffn)
+    MW_SK(1, 4);    // 128   (test dims)
+    MW_SK(1, 8);    // 256
+#undef MW_SK
     dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
     skinny_gemm_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias, resid,
                                              out, ldo, R, N, K, flags);
@@ -210,6 +300,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     __shared__ float red_s[8];
     const int h = blockIdx.x, r = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int UNR = SELF ? 4 : 8;             // independent 16-byte loads in flight per thread
     const int lg = lane & 7, kq = lane >> 3;      // 8 lanes per key, 4 keys per warp instruction
     const int seq0 = r / rows_per_seq;
     int n_keys = n_keys_fixed;
@@ -235,11 +326,11 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     }
     // ---- scores
     float mx = -INFINITY;
-    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 64) {   // warp-uniform trip count (shuffles inside)
+    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 16 * UNR) {   // warp-uniform trip count (shuffles inside)
         const int key0 = kbase0 + kq;
-        uint4 kv[4];
+        uint4 kv[UNR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const int key = key0 + 16 * u;
             if (key < n_keys) {
                 const int seq = idx ? ((key == n_keys - 1) ? r : idx[key]) : (SELF ? r : seq0);
@@ -247,7 +338,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const int key = key0 + 16 * u;
             float s = 0.0f;
             if (key < n_keys) {
@@ -285,11 +376,11 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 64) {
+    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 16 * UNR) {
         const int key0 = kbase0 + kq;
-        uint4 vv[4];
+        uint4 vv[UNR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const int key = key0 + 16 * u;
             if (key < n_keys) {
                 const int seq = idx ? ((key == n_keys - 1) ? r : idx[key]) : (SELF ? r : seq0);
@@ -297,7 +388,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             const int key = key0 + 16 * u;
             if (key < n_keys) {
                 const float p = sc[key];
@@ -798,20 +889,25 @@ mw_status cross_kv_project(mw_model* m, const void* d_enc, int B, cudaStream_t s
 }
 
 // one decoder step up to (and excluding) the logits; `beam_phase` selects the self-index table to read
-mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream_t st) {
+enum { PART_EMBED = 1, PART_LN = 2, PART_GEMM = 4, PART_SELF = 8, PART_CROSS = 16, PART_LOGITS = 32, PART_SELECT = 64, PART_ALL = 127 };
+
+mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream_t st, int parts = PART_ALL) {
     const mw_model_config& c = m->cfg;
     DecoderState* s = m->dec;
     const int d = c.d_model, ctx = c.n_text_ctx, T = c.n_audio_ctx;
     mw_status r;
-    embed_kernel<<<R, 128, 0, st>>>(s->cur_tok, (const __nv_bfloat16*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), s->ctl, s->x, d);
-    MW_LAUNCH_CHECK();
+    if (parts & PART_EMBED) {
+        embed_kernel<<<R, 128, 0, st>>>(s->cur_tok, (const __nv_bfloat16*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), s->ctl, s->x, d);
+        MW_LAUNCH_CHECK();
+    }
     const int* idx = beam > 1 ? s->self_idx[idx_phase] : nullptr;
     for (int l = 0; l < c.dec_layers; ++l) {
         auto W = [&](int id) { return m->dlw(l, id); };
         auto F = [&](int id) { return (const float*)m->dlw(l, id); };
-        if ((r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
-        if ((r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st)) != MW_OK) return r;
-        {
+        const bool LN = parts & PART_LN, GM = parts & PART_GEMM;
+        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st)) != MW_OK) return r;
+        if (parts & PART_SELF) {
             __nv_bfloat16* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
             __nv_bfloat16* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
             dim3 grid(c.n_heads, R);
@@ -819,20 +915,20 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                 s->qkv, 3 * d, kc, vc, d, ctx, idx, ctx, s->ctl, 0, 1, s->qkv + d, s->qkv + 2 * d, 3 * d, s->att, d);
             MW_LAUNCH_CHECK();
         }
-        if ((r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
-        if ((r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
-        if ((r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st)) != MW_OK) return r;
-        {
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st)) != MW_OK) return r;
+        if (parts & PART_CROSS) {
             __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             dim3 grid(c.n_heads, R);
             decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(
                 s->qx, d, kv, kv + d, 2 * d, T, nullptr, ctx, s->ctl, T, beam, nullptr, nullptr, 0, s->att, d);
             MW_LAUNCH_CHECK();
         }
-        if ((r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
-        if ((r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
-        if ((r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st)) != MW_OK) return r;
-        if ((r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st)) != MW_OK) return r;
     }
     return MW_OK;
 }
@@ -1193,6 +1289,41 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
     MW_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    *h_ms_avg = ms / iters;
+    return MW_OK;
+}
+
+// ---- measurement hook: average ms of one decode step restricted to the kernel classes in `parts`
+// (1 embed, 2 LayerNorm, 4 skinny GEMMs, 8 self-attention, 16 cross-attention, 32 logits GEMM, 64 select), replayed as a CUDA graph.
+extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, float* h_ms_avg, void* stream) {
+    MW_REQUIRE(m && h_ms_avg && iters > 0, "mw_bench_step: bad argument");
+    const mw_model_config& c = m->cfg;
+    DecoderState* s = m->dec;
+    MW_REQUIRE(B > 0 && B <= c.max_batch, "mw_bench_step: B outside 1..max_batch");
+    mw::DeviceGuard guard(c.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    MW_CUDA_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(DecCtl), st));
+    MW_CUDA_CHECK(cudaMemsetAsync(s->cur_tok, 0, B * 4, st));
+    cudaGraphExec_t g = nullptr;
+    mw_status r = capture_graph(s, &g, [&](cudaStream_t cs) -> mw_status {
+        mw_status q = enqueue_layers(m, B, 1, 0, cs, parts);
+        if (q != MW_OK) return q;
+        if ((parts & PART_LOGITS) && (q = enqueue_logits(m, B, cs)) != MW_OK) return q;
+        return MW_OK;
+    });
+    if (r != MW_OK) return r;
+    cudaEvent_t e0, e1;
+    MW_CUDA_CHECK(cudaEventCreate(&e0));
+    MW_CUDA_CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) MW_CUDA_CHECK(cudaGraphLaunch(g, st));
+    MW_CUDA_CHECK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) MW_CUDA_CHECK(cudaGraphLaunch(g, st));
+    MW_CUDA_CHECK(cudaEventRecord(e1, st));
+    MW_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MW_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaGraphExecDestroy(g);
     *h_ms_avg = ms / iters;
     return MW_OK;
 }

@@ -202,6 +202,13 @@ class Engine:
                    "mw_bench_kernel")
         return float(ms.value)
 
+    def bench_step(self, B: int, parts: int, iters: int = 20) -> float:
+        """Average ms of one decode step restricted to some kernel classes (mw_bench_step)."""
+        ms = C.c_float(0.0)
+        _lib.check(self.lib.mw_bench_step(self.handle, int(B), int(parts), int(iters), C.byref(ms), self._stream()),
+                   "mw_bench_step")
+        return float(ms.value)
+
     def detect_language(self, enc: torch.Tensor, tokens: SpecialTokens) -> np.ndarray:
         B = enc.shape[0]
         probs = np.zeros((B, tokens.n_langs), dtype=np.float32)
