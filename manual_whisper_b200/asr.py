@@ -98,11 +98,14 @@ class WhisperModel:
     """The role of whisperx.asr.WhisperModel(faster_whisper.WhisperModel): one engine replica + batched generate."""
 
     def __init__(self, dims: ModelDims, state_dict, device_index: int = 0, max_batch: int = 32, max_beam: int = 5,
-                 tokens: Optional[SpecialTokens] = None):
+                 tokens: Optional[SpecialTokens] = None, share_weights_with: Optional["WhisperModel"] = None):
         self.dims = dims
         self.tokens = tokens or special_tokens(dims.vocab)
         self.device = torch.device("cuda", device_index)
-        self.engine = Engine(dims, state_dict, self.device, max_batch=max_batch, max_beam=max_beam)
+        packed = share_weights_with.engine.weights if share_weights_with is not None else None
+        self.engine = Engine(dims, state_dict, self.device, max_batch=max_batch, max_beam=max_beam, packed=packed)
+        # every replica drives its own stream so that several batches can be in flight on one GPU
+        self.stream = torch.cuda.Stream(device=self.device) if share_weights_with is not None else None
         self.max_length = dims.n_text_ctx
         self.feat_kwargs = {"feature_size": dims.n_mels}
         self.is_multilingual = True
@@ -261,15 +264,39 @@ class FasterWhisperPipeline:
         return segments
 
     # ---- batched execution over one or more replicas
-    def _run_batches(self, audio, offs, lens, batch_size, options, print_progress, combined_progress, forced_eot_len):
+    def upload(self, audio: np.ndarray, offs: np.ndarray, lens: np.ndarray) -> Dict:
+        """One H2D copy per GPU of the span of the waveform the windows cover (pinned staging)."""
+        lo = int(offs.min())
+        hi = int((offs + lens).max())
+        host = torch.from_numpy(audio[lo:hi])
+        if not host.is_pinned():
+            try:
+                host = host.pin_memory()
+            except RuntimeError:
+                pass
+        out = {}
+        for dev in {rep.device for rep in self.replicas}:
+            with torch.cuda.device(dev):
+                out[dev] = host.to(dev, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+        return {"lo": lo, "audio": out}
+
+    def run_device_batches(self, resident: Dict, offs, lens, batch_size, options=None, print_progress=False,
+                           combined_progress=False, forced_eot_len=0, batch_order: Optional[Sequence[int]] = None):
+        """Transcribes windows whose audio is already resident in HBM.  Batches are handed out dynamically to the
+        replicas (one host thread + one stream each); results come back in window order."""
+        options = options or self.options
         n = len(offs)
         batches = [(i, min(i + batch_size, n)) for i in range(0, n, batch_size)]
+        if batch_order is not None:
+            batches = [batches[i] for i in batch_order]
         out: List = [None] * n
         tokenizer = self.tokenizer
-        n_rep = min(len(self.replicas), len(batches))
+        n_rep = max(1, min(len(self.replicas), len(batches)))
         errors: List[BaseException] = []
-        done = [0]
+        state = {"next": 0, "done": 0}
         lock = threading.Lock()
+        lo = resident["lo"]
 
         def worker(rep_idx: int):
             rep = self.replicas[rep_idx]
@@ -277,28 +304,27 @@ class FasterWhisperPipeline:
                 with torch.cuda.device(rep.device):
                     if batch_size > rep.engine.max_batch:
                         raise ValueError(f"batch_size={batch_size} exceeds the replica's max_batch={rep.engine.max_batch}")
-                    mine = batches[rep_idx::n_rep]
-                    lo = min(offs[a] for a, _ in mine)
-                    hi = max(int(offs[b - 1]) + int(lens[b - 1]) for _, b in mine)
-                    # one H2D copy of the span this replica needs (pinned staging)
-                    host = torch.from_numpy(audio[lo:hi])
-                    if not host.is_pinned():
-                        try:
-                            host = host.pin_memory()
-                        except RuntimeError:
-                            pass
-                    d_audio = host.to(rep.device, non_blocking=True)
-                    for a, b in mine:
-                        d_off = torch.from_numpy(offs[a:b] - lo).to(rep.device)
-                        d_len = torch.from_numpy(lens[a:b]).to(rep.device)
-                        texts, toks = rep.transcribe_windows(d_audio, d_off, d_len, tokenizer, options, forced_eot_len)
-                        for k in range(b - a):
-                            out[a + k] = (texts[k], toks[k])
-                        with lock:
-                            done[0] += b - a
-                            if print_progress:
-                                pct = done[0] / n * 100
-                                print(f"Progress: {pct / 2 if combined_progress else pct:.2f}%...")
+                    stream = rep.stream if (rep.stream is not None and n_rep > 1) else torch.cuda.current_stream(rep.device)
+                    d_audio = resident["audio"][rep.device]
+                    with torch.cuda.stream(stream):
+                        while True:
+                            with lock:
+                                i = state["next"]
+                                state["next"] += 1
+                            if i >= len(batches):
+                                break
+                            a, b = batches[i]
+                            d_off = torch.from_numpy(offs[a:b] - lo).to(rep.device, non_blocking=True)
+                            d_len = torch.from_numpy(np.ascontiguousarray(lens[a:b], dtype=np.int32)).to(rep.device, non_blocking=True)
+                            texts, toks = rep.transcribe_windows(d_audio, d_off, d_len, tokenizer, options, forced_eot_len)
+                            for k in range(b - a):
+                                out[a + k] = (texts[k], toks[k])
+                            with lock:
+                                state["done"] += b - a
+                                if print_progress:
+                                    pct = state["done"] / n * 100
+                                    print(f"Progress: {pct / 2 if combined_progress else pct:.2f}%...")
+                        stream.synchronize()
             except BaseException as e:      # surfaced on the calling thread
                 errors.append(e)
 
@@ -315,13 +341,18 @@ class FasterWhisperPipeline:
         self.last_stats = {"windows": n, "batches": len(batches), "replicas": n_rep}
         return out
 
+    def _run_batches(self, audio, offs, lens, batch_size, options, print_progress, combined_progress, forced_eot_len):
+        resident = self.upload(audio, offs, lens)
+        return self.run_device_batches(resident, offs, lens, batch_size, options, print_progress, combined_progress,
+                                       forced_eot_len)
+
 
 def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str = "float16",
                asr_options: Optional[dict] = None, language: Optional[str] = None, vad_model=None,
                vad_method: Optional[str] = "pyannote", vad_options: Optional[dict] = None,
                model: Optional[Union[WhisperModel, dict]] = None, task: str = "transcribe",
                download_root: Optional[str] = None, local_files_only: bool = False, threads: int = 4,
-               *, max_batch: int = 32, init_scheme: str = "survey", init_seed: int = 1234,
+               *, max_batch: int = 32, streams_per_device: int = 2, init_scheme: str = "survey", init_seed: int = 1234,
                dims: Optional[ModelDims] = None, tokens: Optional[SpecialTokens] = None,
                tokenizer_file: Optional[str] = None) -> FasterWhisperPipeline:
     """``whisperx.load_model`` for the B200 engine.
@@ -331,7 +362,8 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
     constant (/root/reference/README.md:101) — there is no CPU path here.  ``compute_type`` is accepted for
     signature parity; the engine always computes in bf16 with fp32 accumulation.  ``model`` may be a ready
     WhisperModel or an HF-named state dict; with neither, seeded random-init weights are used because no
-    checkpoint can be downloaded offline (a warning says so).  Keyword-only arguments are additions.
+    checkpoint can be downloaded offline (a warning says so).  Keyword-only arguments are additions;
+    ``streams_per_device`` replicas per GPU share one copy of the weights and keep that many batches in flight.
     """
     if whisper_arch.endswith(".en"):
         language = "en"
@@ -366,8 +398,16 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
             warnings.warn(f"no '{whisper_arch}' checkpoint is reachable offline: using seeded random-init weights "
                           f"(scheme={init_scheme!r}, seed={init_seed}); transcripts are token ids, not text")
             sd = random_init(mdims, seed=init_seed, scheme=init_scheme)
-        replicas = [WhisperModel(mdims, sd, device_index=i, max_batch=max_batch, max_beam=max_beam, tokens=toks)
-                    for i in indices]
+        replicas = []
+        for i in indices:
+            first = WhisperModel(mdims, sd, device_index=i, max_batch=max_batch, max_beam=max_beam, tokens=toks)
+            first.stream = torch.cuda.Stream(device=first.device) if streams_per_device > 1 else None
+            replicas.append(first)
+            # extra replicas on the same GPU share the weights and add a workspace + stream each, so that the launch
+            # gaps of one batch's decode steps are filled by another batch's kernels
+            for _ in range(max(1, int(streams_per_device)) - 1):
+                replicas.append(WhisperModel(mdims, None, device_index=i, max_batch=max_batch, max_beam=max_beam,
+                                             tokens=toks, share_weights_with=first))
 
     tokenizer = None
     if language is not None:

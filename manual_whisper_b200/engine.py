@@ -87,8 +87,10 @@ class GenerationResult:
 class Engine:
     """One Whisper replica on one GPU."""
 
-    def __init__(self, dims: ModelDims, state_dict: Dict[str, torch.Tensor], device=0, max_batch: int = 32,
-                 max_beam: int = 1):
+    def __init__(self, dims: ModelDims, state_dict: Optional[Dict[str, torch.Tensor]], device=0, max_batch: int = 32,
+                 max_beam: int = 1, packed: Optional[List[torch.Tensor]] = None):
+        """`packed` = the weight table of another Engine on the same device (weights are borrowed pointers, so
+        several engines — each with its own workspace — can share one copy)."""
         self.lib = _lib.load()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if dev.type != "cuda":
@@ -98,7 +100,11 @@ class Engine:
         self.max_batch = int(max_batch)
         self.max_beam = int(max_beam)
         with torch.cuda.device(self.device):
-            self.weights = pack_weights(state_dict, dims, self.device)
+            if packed is not None:
+                assert all(t.device == self.device for t in packed)
+                self.weights = packed
+            else:
+                self.weights = pack_weights(state_dict, dims, self.device)
             torch.cuda.synchronize()
         ptrs = (C.c_void_p * len(self.weights))(*[t.data_ptr() for t in self.weights])
         table = _lib.WeightTableC(len(self.weights), C.cast(ptrs, C.POINTER(C.c_void_p)))
