@@ -17,6 +17,9 @@ using namespace mw::logmel;
 
 namespace {
 
+constexpr int MAX_SM_MELS = 128;
+constexpr int MAX_SM_W = 1536;
+
 struct TileSmem {
     cpx Y[FR * 200];          // 51200 B
     float stage[STAGE_N];     // 21440 B
@@ -25,6 +28,10 @@ struct TileSmem {
     cpx tw200[200];           // 1600 B
     cpx tw400[N_FREQ + 1];    // 1616 B
     float red[NT / 32];
+    // sparse filterbank, resident for the CTA's lifetime (a warp walks one mel row at a time: keeping these in
+    // shared memory removes a chain of dependent global loads per row)
+    int mel_lo[MAX_SM_MELS], mel_cnt[MAX_SM_MELS], mel_off[MAX_SM_MELS];
+    float mel_w[MAX_SM_W];
 };
 
 __device__ __forceinline__ unsigned ordered_bits(float f) {
@@ -35,30 +42,19 @@ __device__ __forceinline__ float from_ordered_bits(unsigned b) {
     return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
 }
 
+// Persistent: grid = min(#tiles, 2 x SMs); a CTA loads the constant tables once and then walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... (tile t = 32 frames of chunk t / tiles_per_chunk).
 __global__ void __launch_bounds__(NT, 2)
 logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
                    const int64_t* __restrict__ offsets, const int32_t* __restrict__ lengths,
-                   int64_t single_len, int64_t padded, int64_t n_frames, int n_mels,
+                   int64_t single_len, int64_t padded, int64_t n_frames, int n_mels, int n_chunks,
                    const float* __restrict__ tables,   // win[400] | tw200[200*2] | tw400[202*2]
                    const int* __restrict__ mel_lo, const int* __restrict__ mel_cnt,
-                   const int* __restrict__ mel_off, const float* __restrict__ mel_w,
+                   const int* __restrict__ mel_off, const float* __restrict__ mel_w, int mel_nnz,
                    float* __restrict__ out, unsigned* __restrict__ gmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.y;
-    const int64_t frame0 = (int64_t)blockIdx.x * FR;
-
-    int64_t off = 0, len = single_len;
-    if (offsets) {
-        off = offsets[chunk];
-        len = lengths[chunk];
-        if (off < 0) off = 0;
-        if (off > n_audio) off = n_audio;
-        if (len > n_audio - off) len = n_audio - off;
-        if (len > padded) len = padded;
-        if (len < 0) len = 0;
-    }
     // constant tables -> shared (divergent indices would serialise in the constant cache)
     for (int i = tid; i < N_FFT; i += NT) s.win[i] = tables[i];
     {
@@ -66,25 +62,53 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
         for (int i = tid; i < 200; i += NT) { float2 v = t2[i]; s.tw200[i] = {v.x, v.y}; }
         for (int i = tid; i < N_FREQ; i += NT) { float2 v = t2[200 + i]; s.tw400[i] = {v.x, v.y}; }
     }
-    stage_load(tid, s.stage, audio + off, len, padded, frame0);
-    __syncthreads();
-    stage_radix8(tid, s.stage, s.win, s.tw200, s.Y);
-    __syncthreads();
-    stage_radix25(tid, s.Y);
-    __syncthreads();
-    stage_power(tid, s.Y, s.tw400, s.P);
-    __syncthreads();
-    float vmax = stage_mel(tid, s.P, n_mels, mel_lo, mel_cnt, mel_off, mel_w,
-                           out + (int64_t)chunk * n_mels * n_frames, n_frames, frame0, n_frames, -INFINITY);
+    const bool sm_tables = n_mels <= MAX_SM_MELS && mel_nnz <= MAX_SM_W;
+    if (sm_tables) {
+        for (int i = tid; i < n_mels; i += NT) { s.mel_lo[i] = mel_lo[i]; s.mel_cnt[i] = mel_cnt[i]; s.mel_off[i] = mel_off[i]; }
+        for (int i = tid; i < mel_nnz; i += NT) s.mel_w[i] = mel_w[i];
+    }
+    const int* p_lo = sm_tables ? s.mel_lo : mel_lo;
+    const int* p_cnt = sm_tables ? s.mel_cnt : mel_cnt;
+    const int* p_off = sm_tables ? s.mel_off : mel_off;
+    const float* p_w = sm_tables ? s.mel_w : mel_w;
+    const int64_t tiles_per_chunk = (n_frames + FR - 1) / FR;
+    const int64_t n_tiles = tiles_per_chunk * n_chunks;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int chunk = (int)(t / tiles_per_chunk);
+        const int64_t frame0 = (t - chunk * tiles_per_chunk) * FR;
+        int64_t off = 0, len = single_len;
+        if (offsets) {
+            off = offsets[chunk];
+            len = lengths[chunk];
+            if (off < 0) off = 0;
+            if (off > n_audio) off = n_audio;
+            if (len > n_audio - off) len = n_audio - off;
+            if (len > padded) len = padded;
+            if (len < 0) len = 0;
+        }
+        if (tile_is_interior(audio + off, len, padded, frame0)) stage_load_fast(tid, s.stage, audio + off + (frame0 * HOP - N_FFT / 2));
+        else stage_load(tid, s.stage, audio + off, len, padded, frame0);
+        __syncthreads();
+        stage_radix8(tid, s.stage, s.win, s.tw200, s.Y);
+        __syncthreads();
+        stage_radix25(tid, s.Y);
+        __syncthreads();
+        stage_power(tid, s.Y, s.tw400, s.P);
+        __syncthreads();
+        float vmax = stage_mel(tid, s.P, n_mels, p_lo, p_cnt, p_off, p_w, out + (int64_t)chunk * n_mels * n_frames, n_frames,
+                               frame0, n_frames, -INFINITY);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if ((tid & 31) == 0) s.red[tid >> 5] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = s.red[0];
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if ((tid & 31) == 0) s.red[tid >> 5] = vmax;
+        __syncthreads();
+        if (tid == 0) {
+            float m = s.red[0];
 #pragma unroll
-        for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, s.red[w]);
-        atomicMax(gmax + chunk, ordered_bits(m));
+            for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, s.red[w]);
+            atomicMax(gmax + chunk, ordered_bits(m));
+        }
+        // the next tile's first shared-memory writes (stage) are separated from this tile's last reads (P, red) by
+        // the barrier above and the one after its load stage
     }
 }
 
@@ -140,6 +164,8 @@ struct mw_logmel_plan {
     int* d_cnt = nullptr;
     int* d_off = nullptr;
     float* d_w = nullptr;
+    int nnz = 0;
+    int sm_count = 148;
     unsigned* d_gmax = nullptr;
 };
 
@@ -177,7 +203,10 @@ extern "C" mw_status mw_logmel_plan_create(int n_mels, const float* h_filters, i
         off[m] = (int)w.size();
         for (int k = 0; k < cnt[m]; ++k) w.push_back(h_filters[m * N_FREQ + lo[m] + k]);
     }
+    p->nnz = (int)w.size();
     if (w.empty()) w.push_back(0.0f);
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (p->sm_count <= 0) p->sm_count = 148;
     MW_CUDA_CHECK(cudaMalloc(&p->d_tables, tab.size() * sizeof(float)));
     MW_CUDA_CHECK(cudaMalloc(&p->d_lo, n_mels * sizeof(int)));
     MW_CUDA_CHECK(cudaMalloc(&p->d_cnt, n_mels * sizeof(int)));
@@ -213,9 +242,11 @@ static mw_status run_logmel(mw_logmel_plan* p, const float* d_audio, int64_t n_a
     mw::DeviceGuard guard(p->device);
     MW_CUDA_CHECK(cudaMemsetAsync(p->d_gmax, 0, n_chunks * sizeof(unsigned), st));
     dim3 grid((unsigned)tiles, (unsigned)n_chunks);
-    logmel_tile_kernel<<<grid, NT, sizeof(TileSmem), st>>>(d_audio, n_audio, d_offsets, d_lengths, single_len, padded,
-                                                          n_frames, p->n_mels, p->d_tables, p->d_lo, p->d_cnt,
-                                                          p->d_off, p->d_w, d_out, p->d_gmax);
+    const int64_t total_tiles = tiles * n_chunks;
+    const unsigned persistent = (unsigned)(total_tiles < 2LL * p->sm_count ? total_tiles : 2LL * p->sm_count);
+    logmel_tile_kernel<<<persistent, NT, sizeof(TileSmem), st>>>(d_audio, n_audio, d_offsets, d_lengths, single_len, padded,
+                                                                n_frames, p->n_mels, n_chunks, p->d_tables, p->d_lo, p->d_cnt,
+                                                                p->d_off, p->d_w, p->nnz, d_out, p->d_gmax);
     MW_LAUNCH_CHECK();
     logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (__nv_bfloat16*)d_out_t);
     MW_LAUNCH_CHECK();

@@ -51,7 +51,10 @@ int main(int argc, char** argv) {
     std::vector<float> stage(STAGE_N), P(FR * PS);
     float gmax = -INFINITY;
     for (long f0 = 0; f0 < n_frames; f0 += FR) {
-        for (int t = 0; t < NT; ++t) stage_load(t, stage.data(), audio.data(), len, padded, f0);
+        if (tile_is_interior(audio.data(), len, padded, f0))
+            for (int t = 0; t < NT; ++t) stage_load_fast(t, stage.data(), audio.data() + (f0 * HOP - N_FFT / 2));
+        else
+            for (int t = 0; t < NT; ++t) stage_load(t, stage.data(), audio.data(), len, padded, f0);
         for (int t = 0; t < NT; ++t) stage_radix8(t, stage.data(), win.data(), tw200.data(), Y.data());
         for (int t = 0; t < NT; ++t) stage_radix25(t, Y.data());
         for (int t = 0; t < NT; ++t) stage_power(t, Y.data(), tw400.data(), P.data());
