@@ -3,12 +3,12 @@
 // (SURVEY.md §8 a6, A.7).
 //
 // One CTA = one (batch, head, 128-query tile); 128 threads, thread i owns query row i.
-//   S = Q K_j^T        tcgen05.mma 128x128x64  (Q, K_j: TMA, K-major SWIZZLE_128B)       -> TMEM cols [0,128)
-//   softmax            thread reads its S row with tcgen05.ld (two passes: max, then exp2), writes the
+//   S = Q K_j^T        tcgen05.mma 128x64x64   (Q, K_j: TMA, K-major SWIZZLE_128B)        -> TMEM cols [0,64)
+//   softmax            thread reads its S row (64 fp32) with tcgen05.ld, max / exp2 in registers, writes the
 //                      un-normalised P as bf16 into 128B-swizzled shared memory (A operand of the next MMA)
-//   O_j = P V_j        tcgen05.mma 128x64x128  (V_j: TMA tile [keys, d] used MN-major)     -> TMEM cols [128,192)
+//   O_j = P V_j        tcgen05.mma 128x64x64   (V_j: TMA tile [keys, d] used MN-major)      -> TMEM cols [64,128)
 //   acc = acc*alpha + O_j in registers (fp32), final acc / l -> bf16.
-// Two CTAs fit per SM (96 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Four CTAs fit per SM (48 KB smem, 128 TMEM columns each), so one CTA's softmax overlaps the others' MMAs.
 #include "gemm.cuh"
 #include "ptx_sm100.cuh"
 
@@ -18,10 +18,13 @@ using namespace ptx;
 namespace {
 
 constexpr int TQ = 128;   // queries per CTA
-constexpr int TK = 128;   // keys per block
+constexpr int TK = 64;    // keys per block
 constexpr int DH = 64;
-constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB
-constexpr int ATT_SMEM = 6 * TILE_BYTES + 128 + 1024;   // Q, K0, K1, V, P(2 tiles) + barriers + align slack
+constexpr int Q_BYTES = TQ * DH * 2;       // 16 KB
+constexpr int KV_BYTES = TK * DH * 2;      // 8 KB
+constexpr int P_BYTES = TQ * TK * 2;       // 16 KB: 128 rows x 128 bytes (one swizzle row per query)
+constexpr int ATT_SMEM = Q_BYTES + 2 * KV_BYTES + P_BYTES + 128 + 1024;   // + barriers + alignment slack
+constexpr int ATT_TMEM_COLS = 128;         // S: cols [0,64)   O: cols [64,128)
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -29,22 +32,24 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(128, 2)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out,
-                         int T, int d_model, float scale_log2e) {
+// 4 CTAs per SM (48 KB smem, 128 TMEM columns, <= 128 registers): while one CTA runs its softmax the tensor core
+// serves the others, which is what hides the MMA / mbarrier / tcgen05.ld latencies of the serial per-block chain.
+__global__ void __launch_bounds__(128, 3)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                         __nv_bfloat16* __restrict__ out, int T, int d_model, float scale_log2e) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
-    unsigned char* sK = smem + TILE_BYTES;            // two stages
-    unsigned char* sV = smem + 3 * TILE_BYTES;
-    unsigned char* sP = smem + 4 * TILE_BYTES;        // two 64-key halves
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+    unsigned char* sK = smem + Q_BYTES;
+    unsigned char* sV = sK + KV_BYTES;
+    unsigned char* sP = sV + KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* bar_q = bars;
-    uint64_t* bar_k = bars + 1;   // [2]
-    uint64_t* bar_v = bars + 3;
-    uint64_t* bar_s = bars + 4;
-    uint64_t* bar_o = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* bar_k = bars + 1;
+    uint64_t* bar_v = bars + 2;
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_o = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * TQ;
@@ -53,13 +58,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
     const int col_q = h * DH, col_k = d_model + h * DH, col_v = 2 * d_model + h * DH;
 
     if (tid == 0) {
-        prefetch_tensormap(&tmap_qkv);
-        for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+        prefetch_tensormap(&tmap_q);
+        prefetch_tensormap(&tmap_kv);
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -67,24 +73,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + 128;
+    const uint32_t tmem_o = tmem_base + 64;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_q, TILE_BYTES);
-        tma_load_3d(sQ, &tmap_qkv, bar_q, col_q, q0, b);
-        mbar_arrive_expect_tx(&bar_k[0], TILE_BYTES);
-        tma_load_3d(sK, &tmap_qkv, &bar_k[0], col_k, 0, b);
-        if (n_blocks > 1) {
-            mbar_arrive_expect_tx(&bar_k[1], TILE_BYTES);
-            tma_load_3d(sK + TILE_BYTES, &tmap_qkv, &bar_k[1], col_k, TK, b);
-        }
-        mbar_arrive_expect_tx(bar_v, TILE_BYTES);
-        tma_load_3d(sV, &tmap_qkv, bar_v, col_v, 0, b);
+        mbar_arrive_expect_tx(bar_q, Q_BYTES);
+        tma_load_3d(sQ, &tmap_q, bar_q, col_q, q0, b);
+        mbar_arrive_expect_tx(bar_k, KV_BYTES);
+        tma_load_3d(sK, &tmap_kv, bar_k, col_k, 0, b);
+        mbar_arrive_expect_tx(bar_v, KV_BYTES);
+        tma_load_3d(sV, &tmap_kv, bar_v, col_v, 0, b);
     }
 
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 1);   // B (=V) is MN-major
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, TK, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, 1);   // B (=V) is MN-major
 
     float acc[DH];
 #pragma unroll
@@ -92,13 +94,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
     float m_run = -INFINITY, l_run = 0.0f;
 
     for (int j = 0; j < n_blocks; ++j) {
-        const int ks = j & 1;
         if (tid == 0) {
             if (j == 0) mbar_wait(bar_q, 0);
-            mbar_wait(&bar_k[ks], (j >> 1) & 1);
+            mbar_wait(bar_k, j & 1);
             tc_fence_after();
             const uint64_t dq = make_desc_sw128(smem_u32(sQ), 1024, 0);
-            const uint64_t dk = make_desc_sw128(smem_u32(sK + ks * TILE_BYTES), 1024, 0);
+            const uint64_t dk = make_desc_sw128(smem_u32(sK), 1024, 0);
 #pragma unroll
             for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
             umma_commit(bar_s);
@@ -106,53 +107,56 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
         __syncwarp();
         mbar_wait(bar_s, j & 1);
         tc_fence_after();
-        if (tid == 0 && j + 2 < n_blocks) {      // K stage `ks` is free again
-            mbar_arrive_expect_tx(&bar_k[ks], TILE_BYTES);
-            tma_load_3d(sK + ks * TILE_BYTES, &tmap_qkv, &bar_k[ks], col_k, (j + 2) * TK, b);
+        if (tid == 0 && j + 1 < n_blocks) {      // K buffer is free again: fetch the next block under the softmax
+            mbar_arrive_expect_tx(bar_k, KV_BYTES);
+            tma_load_3d(sK, &tmap_kv, bar_k, col_k, (j + 1) * TK, b);
         }
         __syncwarp();
-        const int key0 = j * TK;
-        const int n_valid = min(TK, T - key0);    // >= 1
-        // ---- pass 1: row max
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < TK; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_s + lane_off + c, r);
-            tmem_ld_wait();
+        const int n_valid = min(TK, T - j * TK);    // >= 1
+        // S row -> registers (64 fp32), max, exp2, bf16 P into the swizzled A-operand tile
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_s + lane_off, r0);
+        tmem_ld32(tmem_s + lane_off + 32, r1);
+        tmem_ld_wait();
+        if (n_valid < TK) {       // last, partial block only: masked keys contribute exp2(-inf) = 0
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) {
+                if (i >= n_valid) r0[i] = 0xff800000u;
+                if (32 + i >= n_valid) r1[i] = 0xff800000u;
+            }
         }
-        const float m_new = fmaxf(m_run, mx);
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four chains for ILP
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(r1[i]));
+            mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
+        }
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
         const float alpha = ex2((m_run - m_new) * scale_log2e);   // m_run = -inf on the first block -> 0
         const float mb = m_new * scale_log2e;
-        // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 P into swizzled smem
-        float lsum = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < TK; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_s + lane_off + c, r);
-            tmem_ld_wait();
+        float ls0 = 0.0f, ls1 = 0.0f, ls2 = 0.0f, ls3 = 0.0f;
+        unsigned char* prow = sP + tid * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
             uint32_t packed[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                float p0 = (c + i < n_valid) ? ex2(fmaf(__uint_as_float(r[i]), scale_log2e, -mb)) : 0.0f;
-                float p1 = (c + i + 1 < n_valid) ? ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2e, -mb)) : 0.0f;
+                const float p0 = ex2(fmaf(__uint_as_float(half ? r1[i] : r0[i]), scale_log2e, -mb));
+                const float p1 = ex2(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), scale_log2e, -mb));
+                if (i & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
                 __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-                // the row sum uses the rounded values the tensor core will see
-                lsum += __low2float(hh) + __high2float(hh);
                 packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            unsigned char* prow = sP + (c >> 6) * TILE_BYTES + tid * 128;
-            const int cbase = ((c & 63) >> 3);       // first 16-byte chunk of this 32-key group inside the 128-byte row
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int chunk = (cbase + g) ^ (tid & 7);
+                const int chunk = (half * 4 + g) ^ (tid & 7);
                 *reinterpret_cast<uint4*>(prow + chunk * 16) =
                     make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
             }
         }
+        const float lsum = (ls0 + ls1) + (ls2 + ls3);
         l_run = l_run * alpha + lsum;
         m_run = m_new;
         fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core's async proxy
@@ -163,8 +167,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TK / 16; ++k) {
-                const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES) + (k & 3) * 32, 1024, 0);
-                const uint64_t dv = make_desc_sw128(smem_u32(sV) + k * 2048, 1024, TILE_BYTES);
+                const uint64_t dp = make_desc_sw128(smem_u32(sP) + k * 32, 1024, 0);
+                const uint64_t dv = make_desc_sw128(smem_u32(sV) + k * 2048, 1024, KV_BYTES);
                 umma_bf16(tmem_o, dp, dv, idesc_o, k ? 1u : 0u);
             }
             umma_commit(bar_o);
@@ -173,17 +177,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
         mbar_wait(bar_o, j & 1);
         tc_fence_after();
         if (tid == 0 && j + 1 < n_blocks) {      // V buffer is free again
-            mbar_arrive_expect_tx(bar_v, TILE_BYTES);
-            tma_load_3d(sV, &tmap_qkv, bar_v, col_v, (j + 1) * TK, b);
+            mbar_arrive_expect_tx(bar_v, KV_BYTES);
+            tma_load_3d(sV, &tmap_kv, bar_v, col_v, (j + 1) * TK, b);
         }
         __syncwarp();
+        tmem_ld32(tmem_o + lane_off, r0);
+        tmem_ld32(tmem_o + lane_off + 32, r1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < DH; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_o + lane_off + c, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], alpha, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) {
+            acc[i] = fmaf(acc[i], alpha, __uint_as_float(r0[i]));
+            acc[32 + i] = fmaf(acc[32 + i], alpha, __uint_as_float(r1[i]));
         }
         tc_fence_before();
     }
@@ -207,7 +211,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, ATT_TMEM_COLS);
     }
 }
 
@@ -216,12 +220,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
 mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_heads, cudaStream_t st) {
     MW_REQUIRE(d_qkv && d_out && B > 0 && T > 0 && n_heads > 0, "attention: bad arguments");
     const int d = n_heads * DH;
-    CUtensorMap tm;
+    CUtensorMap tm_q, tm_kv;
     uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
-    uint32_t box[3] = {DH, 128, 1};
-    mw_status s = encode_tensor_map(&tm, d_qkv, 3, dims, str, box, true);
+    uint32_t box_q[3] = {DH, TQ, 1}, box_kv[3] = {DH, TK, 1};
+    mw_status s = encode_tensor_map(&tm_q, d_qkv, 3, dims, str, box_q, true);
     if (s != MW_OK) return s;
+    if ((s = encode_tensor_map(&tm_kv, d_qkv, 3, dims, str, box_kv, true)) != MW_OK) return s;
     static bool attr_set = false;
     if (!attr_set) {
         MW_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -229,7 +234,7 @@ mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_h
     }
     dim3 grid(ceil_div(T, TQ), n_heads, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;   // d_head^-0.5 * log2(e)
-    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm, (__nv_bfloat16*)d_out, T, d, scale_log2e);
+    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, T, d, scale_log2e);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

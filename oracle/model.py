@@ -54,7 +54,7 @@ class OracleWhisper:
             # the encoder's flash kernel rounds the un-normalised exp() to bf16 before P.V
             m = s.max(dim=-1, keepdim=True).values
             e = _r(torch.exp(s - m), True)
-            o = torch.matmul(e, v) / e.sum(dim=-1, keepdim=True)
+            o = torch.matmul(e, v) / torch.exp(s - m).sum(dim=-1, keepdim=True)
         else:
             o = torch.matmul(p, v)
         B, H, T, D = o.shape

@@ -123,6 +123,23 @@ def test_greedy_ids(which, with_ts, request):
             assert abs(g.scores[0] - r.scores[0]) < 2e-2
 
 
+def _oracle_score(model, enc1, prompt, ids, tok, n_new, length_penalty=1.0):
+    """Length-normalised log-probability the ORACLE assigns to `ids` (rules applied at every step)."""
+    from oracle.generate import apply_rules, expand_suppress
+    with_ts = prompt[-1] != tok.no_timestamps
+    sup = expand_suppress(tok, [-1], with_ts)
+    ended = len(ids) < n_new
+    seq = list(ids) + ([tok.eot] if ended else [])
+    inp = torch.tensor([prompt + seq[:-1]])
+    with torch.no_grad():
+        logits = model.decode(inp, 0, model.cross_kv(enc1), model.new_cache())[0]
+    total = 0.0
+    for i, t in enumerate(seq):
+        row = apply_rules(logits[len(prompt) - 1 + i][None], [seq[:i]], tok, sup, tok.suppress_ids_begin, with_ts, 50)
+        total += float(torch.log_softmax(row.float(), -1)[0, t])
+    return total / (len(seq) ** length_penalty)
+
+
 @pytest.mark.parametrize("with_ts", [False, True])
 @pytest.mark.parametrize("beam,patience", [(5, 1.0), (3, 2.0)])
 def test_beam_ids(small, with_ts, beam, patience):
@@ -137,11 +154,18 @@ def test_beam_ids(small, with_ts, beam, patience):
     same = [g.sequences_ids[0] == r.sequences_ids[0] for g, r in zip(got, ref)]
     print(f"[beam{beam} p={patience} ts={with_ts}] identical {sum(same)}/{len(same)} scores",
           [(round(g.scores[0], 4), round(r.scores[0], 4)) for g, r in zip(got, ref)])
-    # beam search compounds near-ties; require score agreement everywhere and id identity on most windows
-    for g, r in zip(got, ref):
+    # beam search compounds the near-ties of random-init weights: a window may end on a different but equally good
+    # hypothesis.  Required: the engine's own score agrees with the oracle's best score, and the engine's hypothesis
+    # RE-SCORED BY THE ORACLE is as good as the oracle's best one (so it is a legitimate winner, not an error).
+    n_new = dims.n_text_ctx // 2 if len(prompt) <= dims.n_text_ctx // 2 else dims.n_text_ctx - len(prompt)
+    for b, (g, r) in enumerate(zip(got, ref)):
         assert abs(g.scores[0] - r.scores[0]) < 3e-2
         assert g.scores == sorted(g.scores, reverse=True)
-    assert sum(same) >= len(same) - 1
+        if not same[b]:
+            rescored = _oracle_score(emu, enc.float().cpu()[b:b + 1], prompt, g.sequences_ids[0], tok, n_new)
+            print(f"  window {b}: different hypothesis; oracle re-score {rescored:.4f} vs oracle best {r.scores[0]:.4f}")
+            assert rescored >= r.scores[0] - 3e-2
+    assert sum(same) >= len(same) // 2
 
 
 def test_eot_and_forced_eot_and_long_prompt(small):
