@@ -97,3 +97,18 @@ def test_sharded_helper_single_process(setup):
     full = pipe.transcribe(audio, batch_size=4)
     sh = transcribe_sharded(pipe, audio, 4, rank=0, world=1, language="en")
     assert [s["tokens"] for s in sh["segments"]] == [s["tokens"] for s in full["segments"]]
+
+
+def test_batches_in_flight_do_not_change_results(setup):
+    """Two shared-weight replicas on two streams (the default) give the ids of a single replica."""
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    one = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+                        vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=1)
+    three = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+                          vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=3)
+    assert len(one.replicas) == 1 and len(three.replicas) == 3
+    assert three.replicas[1].engine.weights is three.replicas[0].engine.weights        # one copy of the weights
+    a = one.transcribe(audio, batch_size=2)
+    b = three.transcribe(audio, batch_size=2)
+    assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
+    assert three.last_stats["replicas"] == 3
