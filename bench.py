@@ -37,6 +37,8 @@ sys.path.insert(0, ROOT)
 MODEL = "large-v3"
 BATCH = 32
 HOUR_S = 3600.0
+WORKLOAD = (f"{MODEL} (128 mels), 1-hour synthetic 16 kHz recording per GPU, VAD-chunked into <=30 s windows, "
+            f"batch_size={BATCH}, greedy, 224 tokens/window (random-init weights never emit eot)")
 
 
 def _peaks():
@@ -178,7 +180,7 @@ def run_reference(args):
     line = {"metric": "RTFx (audio-s/wall-s) Whisper large-v3 batched", "impl": "reference", "value": v, "unit": "x real-time",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{MODEL} 1-hour synthetic recording, VAD-chunked, batch_size={BATCH}, greedy (bounded CPU sample)"},
+            "config": {"workload": WORKLOAD, "weights": "random-init N(0,0.02^2) seed 1234", "sample": "bounded CPU sample, see cpu_baseline.sample"},
             "cpu_baseline": {"value": v, "unit": "x real-time", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -313,9 +315,7 @@ def main():
             "unit": "x real-time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{MODEL} (128 mels), 1-hour synthetic 16 kHz recording per GPU, VAD-chunked into "
-                                   f"{len(windows)} windows (mean {float(lens.mean()) / 16000:.1f} s), batch_size={BATCH}, greedy, "
-                                   f"224 tokens/window (random-init weights never emit eot)",
+            "config": {"workload": WORKLOAD, "windows": len(windows), "mean_window_s": float(lens.mean()) / 16000,
                        "weights": "random-init N(0,0.02^2) seed 1234, bf16",
                        "parallelism": f"dp{world} (one process per GPU, {args.streams} batches in flight per GPU)",
                        "l2": "inputs larger than L2 (weights 3.1 GB + cross-K/V 7.9 GB streamed per step)"},
