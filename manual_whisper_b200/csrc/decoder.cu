@@ -416,6 +416,150 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Grouped cross-attention for beam search: the G hypotheses of one chunk attend to the SAME encoder K/V, so one CTA
+// per (head, chunk) streams K and V once and serves all G queries (CTranslate2 instead tiles the encoder output
+// beam_size times).  Same lane mapping as decode_attn_kernel: 16 bytes per lane, 8 lanes per key.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
+                          const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
+                          __nv_bfloat16* __restrict__ out, int ldo) {
+    extern __shared__ float sc[];          // [G][n_keys] scores, then probabilities
+    __shared__ float red[4][G][64];
+    __shared__ float red_s[G][8];
+    constexpr int UNR = 4;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lg = lane & 7, kq = lane >> 3;
+    float qf[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const uint4 u = *reinterpret_cast<const uint4*>(q + (int64_t)(b * G + g) * ldq + h * 64 + lg * 8);
+        bf16x8_to_float(u, qf[g]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qf[g][i] *= 0.125f;
+    }
+    const __nv_bfloat16* kb = kbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
+    const __nv_bfloat16* vb = vbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
+    float mx[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) mx[g] = -INFINITY;
+    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 16 * UNR) {
+        const int key0 = kbase0 + kq;
+        uint4 kv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int key = key0 + 16 * u;
+            if (key < n_keys) kv[u] = *reinterpret_cast<const uint4*>(kb + (int64_t)key * key_stride);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int key = key0 + 16 * u;
+            float kf[8];
+            if (key < n_keys) bf16x8_to_float(kv[u], kf);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float s = 0.0f;
+                if (key < n_keys) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s = fmaf(qf[g][i], kf[i], s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (key < n_keys) {
+                    if (lg == 0) sc[g * n_keys + key] = s;
+                    mx[g] = fmaxf(mx[g], s);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+        if (lane == 0) red_s[g][warp] = mx[g];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float m = fmaxf(fmaxf(red_s[g][0], red_s[g][1]), fmaxf(red_s[g][2], red_s[g][3]));
+        float a = 0.0f;
+        for (int key = tid; key < n_keys; key += 128) {
+            const float p = __expf(sc[g * n_keys + key] - m);
+            sc[g * n_keys + key] = p;
+            a += p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red_s[g][4 + warp] = a;
+    }
+    __syncthreads();
+    float acc[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g][i] = 0.0f;
+    for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 16 * UNR) {
+        const int key0 = kbase0 + kq;
+        uint4 vv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int key = key0 + 16 * u;
+            if (key < n_keys) vv[u] = *reinterpret_cast<const uint4*>(vb + (int64_t)key * key_stride);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int key = key0 + 16 * u;
+            if (key < n_keys) {
+                float vf[8];
+                bf16x8_to_float(vv[u], vf);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float p = sc[g * n_keys + key];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(p, vf[i], acc[g][i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[g][i] += __shfl_xor_sync(0xffffffffu, acc[g][i], 8);
+            acc[g][i] += __shfl_xor_sync(0xffffffffu, acc[g][i], 16);
+        }
+        if (kq == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][g][lg * 8 + i] = acc[g][i];
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < G * 64; o += 128) {
+        const int g = o >> 6, dcol = o & 63;
+        const float v = ((red[0][g][dcol] + red[1][g][dcol]) + (red[2][g][dcol] + red[3][g][dcol])) / ((red_s[g][4] + red_s[g][5]) + (red_s[g][6] + red_s[g][7]));
+        out[(int64_t)(b * G + g) * ldo + h * 64 + dcol] = __float2bfloat16(v);
+    }
+}
+
+template <int G>
+mw_status launch_cross_grouped(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int64_t key_stride,
+                               int n_keys, __nv_bfloat16* out, int ldo, int n_heads, int B, cudaStream_t st) {
+    const size_t smem = (size_t)G * n_keys * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MW_CUDA_CHECK(cudaFuncSetAttribute(cross_attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    MW_REQUIRE(smem <= 96 * 1024, "cross attention: %zu bytes of scores exceed shared memory", smem);
+    cross_attn_grouped_kernel<G><<<dim3(n_heads, B), 128, smem, st>>>(q, ldq, k, v, key_stride, n_keys, out, ldo);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // logit rules (timestamp rules as transformers/generation/logits_process.py:1996-2043)
 // ------------------------------------------------------------------------------------------------
 struct RowRule {
@@ -920,10 +1064,21 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
         if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st)) != MW_OK) return r;
         if (parts & PART_CROSS) {
             __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
-            dim3 grid(c.n_heads, R);
-            decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(
-                s->qx, d, kv, kv + d, 2 * d, T, nullptr, ctx, s->ctl, T, beam, nullptr, nullptr, 0, s->att, d);
-            MW_LAUNCH_CHECK();
+            if (beam > 1) {
+                const int Bc = R / beam;
+#define MW_XG(g) case g: r = launch_cross_grouped<g>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d, c.n_heads, Bc, st); break
+                switch (beam) {
+                    MW_XG(2); MW_XG(3); MW_XG(4); MW_XG(5); MW_XG(6); MW_XG(7); MW_XG(8);
+                    default: r = MW_ERR_UNSUPPORTED; set_error("beam_size %d unsupported", beam);
+                }
+#undef MW_XG
+                if (r != MW_OK) return r;
+            } else {
+                dim3 grid(c.n_heads, R);
+                decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(
+                    s->qx, d, kv, kv + d, 2 * d, T, nullptr, ctx, s->ctl, T, beam, nullptr, nullptr, 0, s->att, d);
+                MW_LAUNCH_CHECK();
+            }
         }
         if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
