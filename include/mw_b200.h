@@ -179,6 +179,10 @@ mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_
 mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
                        int rows, int d, void* stream);
 
+/* VAD front end: RMS of consecutive frames of `frame` samples, d_out float32 [n / frame].
+ * Feeds the energy VAD so the waveform is uploaded once and never revisited by the host. */
+mw_status mw_frame_rms(const float* d_audio, int64_t n, int frame, float* d_out, void* stream);
+
 /* Measurement hook for bench.py's roofline: average duration (ms, CUDA events on `stream`) of one hot decode
  * kernel launched `iters` times back to back over different layers' data (inputs larger than L2).
  * which: 0 = cross-attention decode, 1 = skinny GEMM (fc1 weights), 2 = skinny GEMM (out-proj weights). */

@@ -9,13 +9,13 @@ imports the CPU oracle, and every call fails loudly if the CUDA library is missi
 from .config import SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES, model_dims, special_tokens
 from .audio import load_audio, log_mel_spectrogram, pad_or_trim, mel_filters
 from .asr import load_model, FasterWhisperPipeline, WhisperModel, TranscriptionOptions, get_prompt
-from .vad import merge_chunks, InjectedVad, EnergyVad, synthetic_speech
+from .vad import merge_chunks, InjectedVad, EnergyVad, GpuEnergyVad, synthetic_speech
 from .tokenizer import Tokenizer
 
 __version__ = "0.1.0"
 __all__ = [
     "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
     "load_audio", "log_mel_spectrogram", "pad_or_trim", "mel_filters", "load_model", "FasterWhisperPipeline",
-    "WhisperModel", "TranscriptionOptions", "get_prompt", "merge_chunks", "InjectedVad", "EnergyVad",
+    "WhisperModel", "TranscriptionOptions", "get_prompt", "merge_chunks", "InjectedVad", "EnergyVad", "GpuEnergyVad",
     "synthetic_speech", "Tokenizer", "model_dims", "special_tokens",
 ]

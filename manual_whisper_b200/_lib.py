@@ -63,6 +63,7 @@ SIGNATURES = {
     "mw_attention_bf16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mw_bench_kernel": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "mw_bench_step": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "mw_frame_rms": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "mw_layernorm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -27,7 +27,7 @@ from .audio import SAMPLE_RATE, N_SAMPLES, N_FRAMES, load_audio
 from .config import ModelDims, SpecialTokens, model_dims, special_tokens, LANGUAGES
 from .engine import Engine, GenerationResult
 from .tokenizer import Tokenizer
-from .vad import EnergyVad, merge_chunks
+from .vad import EnergyVad, GpuEnergyVad, merge_chunks
 from .weights import random_init
 
 
@@ -199,7 +199,13 @@ class FasterWhisperPipeline:
             raise ValueError("audio must be a mono 1-D float array at 16 kHz")
 
         # ---- VAD -> windows
-        waveform = torch.from_numpy(audio).unsqueeze(0)
+        resident = None
+        if getattr(self.vad_model, "wants_device", False):
+            # device-side VAD: one H2D copy of the whole waveform serves the VAD and every ASR batch
+            resident = self.upload(audio, np.array([0], dtype=np.int64), np.array([len(audio)], dtype=np.int64))
+            waveform = resident["audio"][self.device].unsqueeze(0)
+        else:
+            waveform = torch.from_numpy(audio).unsqueeze(0)
         vad_segments = self.vad_model({"waveform": waveform, "sample_rate": SAMPLE_RATE})
         vad_segments = merge_chunks(vad_segments, chunk_size, onset=self._vad_params["vad_onset"],
                                     offset=self._vad_params["vad_offset"])
@@ -207,7 +213,7 @@ class FasterWhisperPipeline:
         language, task = self._prepare_tokenizer(audio, language, task)
         segments = self.transcribe_windows_host(audio, vad_segments, batch_size=batch_size, language=language, task=task,
                                                 print_progress=print_progress, combined_progress=combined_progress,
-                                                verbose=verbose, _forced_eot_len=_forced_eot_len)
+                                                verbose=verbose, _forced_eot_len=_forced_eot_len, _resident=resident)
         if self.preset_language is None:
             self.tokenizer = None
         return {"segments": segments, "language": language}
@@ -228,7 +234,7 @@ class FasterWhisperPipeline:
     def transcribe_windows_host(self, audio: np.ndarray, vad_segments: List[Dict], batch_size: Optional[int] = None,
                                 language: Optional[str] = None, task: Optional[str] = None, print_progress: bool = False,
                                 combined_progress: bool = False, verbose: bool = False, chunk_size: int = 30,
-                                _forced_eot_len: int = 0) -> List[Dict]:
+                                _forced_eot_len: int = 0, _resident: Optional[Dict] = None) -> List[Dict]:
         """The batched loop of ``transcribe`` over an explicit window list (what a rank of the sharded
         multi-process path runs on its share, manual_whisper_b200/distributed.py)."""
         if self.tokenizer is None or (language and language != self.tokenizer.language_code) or \
@@ -254,8 +260,12 @@ class FasterWhisperPipeline:
             lens = (ends - offs).astype(np.int64)
             if (lens > N_SAMPLES).any():
                 raise ValueError("a VAD window is longer than 30 s; the VAD stage must bound turn duration (chunk_size)")
-            results = self._run_batches(audio, offs, lens.astype(np.int32), int(batch_size), options, print_progress,
-                                        combined_progress, _forced_eot_len)
+            if _resident is not None:
+                results = self.run_device_batches(_resident, offs, lens.astype(np.int32), int(batch_size), options,
+                                                  print_progress, combined_progress, _forced_eot_len)
+            else:
+                results = self._run_batches(audio, offs, lens.astype(np.int32), int(batch_size), options, print_progress,
+                                            combined_progress, _forced_eot_len)
             for idx, (text, toks) in enumerate(results):
                 if verbose:
                     print(f"Transcript: [{round(vad_segments[idx]['start'], 3)} --> {round(vad_segments[idx]['end'], 3)}] {text}")
@@ -374,7 +384,7 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
         raise ValueError(f"Requested compute type {compute_type!r} is not a valid compute type")
     if compute_type not in ("bfloat16", "default", "auto"):
         warnings.warn(f"compute_type={compute_type!r} requested; the sm_100a engine computes in bfloat16 with fp32 accumulation")
-    if vad_model is None and vad_method not in ("pyannote", "silero", "energy", None):
+    if vad_model is None and vad_method not in ("pyannote", "silero", "energy", "energy_gpu", None):
         raise ValueError(f"Invalid vad_method: {vad_method}")
     mdims = dims or model_dims(whisper_arch)
     toks = tokens or special_tokens(mdims.vocab)
@@ -422,7 +432,8 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
         if vad_method in ("pyannote", "silero"):
             warnings.warn(f"vad_method={vad_method!r}: the {vad_method} network's weights are not available offline; "
                           "using the built-in energy VAD with the same onset/offset/chunk_size knobs")
-        vad_model = EnergyVad(vad_onset=default_vad_options["vad_onset"], vad_offset=default_vad_options["vad_offset"],
-                              chunk_size=default_vad_options["chunk_size"])
+        cls = GpuEnergyVad if vad_method == "energy_gpu" else EnergyVad
+        vad_model = cls(vad_onset=default_vad_options["vad_onset"], vad_offset=default_vad_options["vad_offset"],
+                        chunk_size=default_vad_options["chunk_size"])
     return FasterWhisperPipeline(model=replicas, vad=vad_model, options=default_asr_options, tokenizer=tokenizer,
                                  language=language, suppress_numerals=suppress_numerals, vad_params=default_vad_options)

@@ -81,6 +81,20 @@ features_to_time_major_kernel(const float* __restrict__ in, __nv_bfloat16* __res
     }
 }
 
+// frame RMS for the energy VAD front end: one warp per frame of `frame` samples
+__global__ void __launch_bounds__(256)
+frame_rms_kernel(const float* __restrict__ audio, int64_t n, int frame, float* __restrict__ out, int64_t n_frames) {
+    const int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= n_frames) return;
+    const float* a = audio + f * frame;
+    float s = 0.0f;
+    for (int i = lane; i < frame; i += 32) { const float v = a[i]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[f] = sqrtf(s / (float)frame + 1e-12f);
+}
+
 }  // namespace
 
 mw_status layernorm_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, int rows, int d,
@@ -108,4 +122,13 @@ mw_status features_to_time_major_launch(const float* in, void* out_bf16, int B, 
 extern "C" mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
                                   int rows, int d, void* stream) {
     return mw::layernorm_launch(d_x, d_gamma, d_beta, d_out_bf16, rows, d, (cudaStream_t)stream);
+}
+
+extern "C" mw_status mw_frame_rms(const float* d_audio, int64_t n, int frame, float* d_out, void* stream) {
+    MW_REQUIRE(d_audio && d_out && frame > 0 && n >= 0, "mw_frame_rms: bad argument");
+    const int64_t n_frames = n / frame;
+    if (n_frames == 0) return MW_OK;
+    mw::frame_rms_kernel<<<(unsigned)((n_frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_audio, n, frame, d_out, n_frames);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
 }

@@ -86,13 +86,19 @@ class EnergyVad:
         self.frame = int(round(frame_s * SAMPLE_RATE))
         self.min_on, self.min_off = min_duration_on, min_duration_off
 
-    def __call__(self, audio: Dict) -> List[SegmentX]:
+    def frame_rms(self, audio: Dict) -> np.ndarray:
         wav = audio["waveform"]
         wav = np.asarray(wav.detach().cpu().numpy() if hasattr(wav, "detach") else wav, dtype=np.float32).reshape(-1)
         n = len(wav) // self.frame
         if n == 0:
+            return np.zeros(0, np.float32)
+        return np.sqrt((wav[: n * self.frame].reshape(n, self.frame) ** 2).mean(axis=1) + 1e-12)
+
+    def __call__(self, audio: Dict) -> List[SegmentX]:
+        e = self.frame_rms(audio)
+        n = len(e)
+        if n == 0:
             return []
-        e = np.sqrt((wav[: n * self.frame].reshape(n, self.frame) ** 2).mean(axis=1) + 1e-12)
         db = 20 * np.log10(e)
         # map energy to a [0, 1] speech score between the noise floor and the loud percentile
         lo, hi = np.percentile(db, 10), np.percentile(db, 95)
@@ -116,6 +122,30 @@ class EnergyVad:
             else:
                 merged.append([a, b])
         return [SegmentX(a, b) for a, b in merged if b - a >= self.min_on]
+
+
+class GpuEnergyVad(EnergyVad):
+    """EnergyVad whose per-frame RMS is computed on the GPU (mw_frame_rms).  `wants_device = True` tells the pipeline to
+    upload the waveform ONCE, run the VAD on the device copy and reuse that copy for the ASR batches (SURVEY.md §8f
+    rank 1: the host never revisits the audio); only n/320 floats come back for the hysteresis pass."""
+    wants_device = True
+
+    def frame_rms(self, audio: Dict) -> np.ndarray:
+        import ctypes as C
+        import torch
+        from . import _lib
+        wav = audio["waveform"]
+        if not (hasattr(wav, "is_cuda") and wav.is_cuda):
+            wav = torch.as_tensor(np.asarray(wav, dtype=np.float32)).cuda()
+        wav = wav.reshape(-1).contiguous()
+        n = wav.numel() // self.frame
+        if n == 0:
+            return np.zeros(0, np.float32)
+        out = torch.empty(n, dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _lib.check(_lib.load().mw_frame_rms(wav.data_ptr(), wav.numel(), self.frame, out.data_ptr(),
+                                                C.c_void_p(torch.cuda.current_stream(wav.device).cuda_stream)), "mw_frame_rms")
+        return out.cpu().numpy()
 
 
 def synthetic_speech(duration_s: float, seed: int = 1, sr: int = SAMPLE_RATE):

@@ -112,3 +112,18 @@ def test_batches_in_flight_do_not_change_results(setup):
     b = three.transcribe(audio, batch_size=2)
     assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
     assert three.last_stats["replicas"] == 3
+
+
+def test_device_side_vad_front_end(setup):
+    """frame energies on the GPU give the same turns as the host VAD and the same transcript."""
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    a = audio[: 16000 * 90]
+    host = mw.EnergyVad()({"waveform": torch.from_numpy(a)[None], "sample_rate": 16000})
+    dev = mw.GpuEnergyVad()({"waveform": torch.from_numpy(a).cuda()[None], "sample_rate": 16000})
+    assert [(round(s.start, 2), round(s.end, 2)) for s in host] == [(round(s.start, 2), round(s.end, 2)) for s in dev]
+    p_host = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, model=sd,
+                           dims=dims, tokens=tok, max_batch=4, vad_method="energy", streams_per_device=1)
+    p_dev = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, model=sd,
+                          dims=dims, tokens=tok, max_batch=4, vad_method="energy_gpu", streams_per_device=1)
+    r1, r2 = p_host.transcribe(a, batch_size=4), p_dev.transcribe(a, batch_size=4)
+    assert [(s["start"], s["end"], s["tokens"]) for s in r1["segments"]] == [(s["start"], s["end"], s["tokens"]) for s in r2["segments"]]

@@ -81,3 +81,18 @@ def test_cuda_stage_code_via_cpu_emulation(name, n_mels, n, padding, logmel_emu,
     got = np.fromfile(tmp_path / "o.f32", np.float32).reshape(n_mels, (n + padding) // 160)
     ref = log_mel_spectrogram(a, n_mels, padding).numpy()
     assert np.abs(got - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,n,padding,n_mels", [("noise", 48000, 0, 128), ("speechlike", 32000, 16000, 80), ("noise", 399, 9601, 128),
+                                                   ("zeros", 16000, 0, 80), ("impulse0", 16000, 0, 128)])
+def test_plain_c_oracle_agrees_with_torch_oracle(name, n, padding, n_mels, tmp_path):
+    """oracle/logmel_ref.c: double-precision direct DFT + its own slaney filterbank, no torch involved."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "oracle_logmel_ref"
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-o", str(exe), os.path.join(root, "oracle", "logmel_ref.c"), "-lm"])
+    a = audio_case(name)[:n]
+    (tmp_path / "a.f32").write_bytes(a.tobytes())
+    subprocess.check_call([str(exe), str(tmp_path / "a.f32"), str(n), str(padding), str(n_mels), str(tmp_path / "o.f32")])
+    got = np.fromfile(tmp_path / "o.f32", np.float32).reshape(n_mels, (n + padding) // 160)
+    assert np.abs(got - log_mel_spectrogram(a, n_mels, padding).numpy()).max() < 1e-4
