@@ -36,7 +36,8 @@ __device__ __forceinline__ float ex2(float x) {
 // serves the others, which is what hides the MMA / mbarrier / tcgen05.ld latencies of the serial per-block chain.
 __global__ void __launch_bounds__(128, 3)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         __nv_bfloat16* __restrict__ out, int T, int d_model, float scale_log2e) {
+                         __nv_bfloat16* __restrict__ out, int Tq, int Tk, int colq0, int colk0, int colv0, int out_ld,
+                         float scale_log2e) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
@@ -54,8 +55,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * TQ;
     const int h = blockIdx.y, b = blockIdx.z;
-    const int n_blocks = (T + TK - 1) / TK;
-    const int col_q = h * DH, col_k = d_model + h * DH, col_v = 2 * d_model + h * DH;
+    const int n_blocks = (Tk + TK - 1) / TK;
+    const int col_q = colq0 + h * DH, col_k = colk0 + h * DH, col_v = colv0 + h * DH;
 
     if (tid == 0) {
         prefetch_tensormap(&tmap_q);
@@ -112,7 +113,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tma_load_3d(sK, &tmap_kv, bar_k, col_k, (j + 1) * TK, b);
         }
         __syncwarp();
-        const int n_valid = min(TK, T - j * TK);    // >= 1
+        const int n_valid = min(TK, Tk - j * TK);    // >= 1
         // S row -> registers (64 fp32), max, exp2, bf16 P into the swizzled A-operand tile
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_s + lane_off, r0);
@@ -193,9 +194,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
 
     const int q = q0 + tid;
-    if (q < T) {
+    if (q < Tq) {
         const float inv = 1.0f / l_run;
-        uint4* o4 = reinterpret_cast<uint4*>(out + ((int64_t)b * T + q) * d_model + h * DH);
+        uint4* o4 = reinterpret_cast<uint4*>(out + ((int64_t)b * Tq + q) * out_ld + h * DH);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             uint32_t w[4];
@@ -217,26 +218,43 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
 }  // namespace
 
-mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_heads, cudaStream_t st) {
-    MW_REQUIRE(d_qkv && d_out && B > 0 && T > 0 && n_heads > 0, "attention: bad arguments");
-    const int d = n_heads * DH;
+// General form: queries [B, Tq, ldq] (head h at column colq0 + 64 h) attend to keys/values [B, Tk, ldkv] (columns
+// colk0 + 64 h / colv0 + 64 h); out [B*Tq, out_ld].  The encoder's self-attention and the decoder's batched-prefill
+// cross-attention are both instances.
+mw_status attention_launch_general(const void* d_q, int64_t ldq, int colq0, const void* d_kv, int64_t ldkv, int colk0, int colv0,
+                                   void* d_out, int out_ld, int B, int Tq, int Tk, int n_heads, cudaStream_t st) {
+    MW_REQUIRE(d_q && d_kv && d_out && B > 0 && Tq > 0 && Tk > 0 && n_heads > 0, "attention: bad arguments");
     CUtensorMap tm_q, tm_kv;
-    uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
-    uint32_t box_q[3] = {DH, TQ, 1}, box_kv[3] = {DH, TK, 1};
-    mw_status s = encode_tensor_map(&tm_q, d_qkv, 3, dims, str, box_q, true);
-    if (s != MW_OK) return s;
-    if ((s = encode_tensor_map(&tm_kv, d_qkv, 3, dims, str, box_kv, true)) != MW_OK) return s;
+    {
+        uint64_t dims[3] = {(uint64_t)ldq, (uint64_t)Tq, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)Tq * ldq * 2};
+        uint32_t box[3] = {DH, TQ, 1};
+        mw_status s = encode_tensor_map(&tm_q, d_q, 3, dims, str, box, true);
+        if (s != MW_OK) return s;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)ldkv, (uint64_t)Tk, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)ldkv * 2, (uint64_t)Tk * ldkv * 2};
+        uint32_t box[3] = {DH, TK, 1};
+        mw_status s = encode_tensor_map(&tm_kv, d_kv, 3, dims, str, box, true);
+        if (s != MW_OK) return s;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         MW_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
-    dim3 grid(ceil_div(T, TQ), n_heads, B);
+    dim3 grid(ceil_div(Tq, TQ), n_heads, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;   // d_head^-0.5 * log2(e)
-    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, T, d, scale_log2e);
+    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, Tq, Tk, colq0, colk0, colv0, out_ld,
+                                                          scale_log2e);
     MW_LAUNCH_CHECK();
     return MW_OK;
+}
+
+mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_heads, cudaStream_t st) {
+    const int d = n_heads * DH;
+    return attention_launch_general(d_qkv, 3 * d, 0, d_qkv, 3 * d, d, 2 * d, d_out, d, B, T, T, n_heads, st);
 }
 
 }  // namespace mw

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 
 namespace mw {
@@ -294,7 +295,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
                    __nv_bfloat16* kbase, __nv_bfloat16* vbase, int64_t key_stride, int64_t keys_per_seq,
                    const int* __restrict__ idx_table, int ctx, const DecCtl* __restrict__ ctl, int n_keys_fixed,
                    int rows_per_seq, const __nv_bfloat16* __restrict__ knew, const __nv_bfloat16* __restrict__ vnew,
-                   int ld_new, __nv_bfloat16* __restrict__ out, int ldo) {
+                   int ld_new, __nv_bfloat16* __restrict__ out, int ldo, int causal_rows = 0) {
     extern __shared__ float sc[];          // scores [n_keys] + reduction scratch
     __shared__ float red[4][64];
     __shared__ float red_s[8];
@@ -304,6 +305,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     const int lg = lane & 7, kq = lane >> 3;      // 8 lanes per key, 4 keys per warp instruction
     const int seq0 = r / rows_per_seq;
     int n_keys = n_keys_fixed;
+    if (!SELF && causal_rows > 0) n_keys = (r % causal_rows) + 1;     // batched prefill: row (b, p) sees keys 0..p
     if (SELF) {
         const int pos = ctl->pos;
         n_keys = pos + 1;
@@ -1134,6 +1136,89 @@ mw_status capture_graph(DecoderState* s, cudaGraphExec_t* out, Fn&& enqueue) {
     return MW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched prefill: the prompt tokens 0..P-2 of all chunks go through the decoder in ONE pass (M = B*(P-1) rows) on
+// the tensor-core GEMM / flash-attention kernels of the encoder, instead of P-1 single-token steps.  What it leaves
+// behind is exactly what the step graph expects: self K/V of positions 0..P-2 in the cache (physical row b*beam,
+// shared by the beams through the index table), pos = step = P-1 and the last prompt token as the next input.
+// Matters for the reference's own call, which passes an initial_prompt (/root/reference/transcribe.py:40,111).
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_prefill_kernel(const int* __restrict__ prompt, const __nv_bfloat16* __restrict__ emb,
+                                     const float* __restrict__ pos_emb, float* __restrict__ x, int Pm, int d) {
+    const int r = blockIdx.x, p = r % Pm;
+    const int tok = prompt[p];
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[(int64_t)r * d + i] = __bfloat162float(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)p * d + i];
+}
+
+__global__ void kv_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc,
+                                  int Pm, int d, int ctx, int beam) {
+    const int r = blockIdx.x, b = r / Pm, p = r - b * Pm;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)r * 3 * d + d);
+    uint4* dk = reinterpret_cast<uint4*>(kc + ((int64_t)(b * beam) * ctx + p) * d);
+    uint4* dv = reinterpret_cast<uint4*>(vc + ((int64_t)(b * beam) * ctx + p) * d);
+    const int nv = d / 8;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) { dk[i] = src[i]; dv[i] = src[nv + i]; }
+}
+
+__global__ void prefill_finish_kernel(const int* __restrict__ prompt, int Pm, int* cur_tok, DecCtl* ctl, int* idx0, int* idx1,
+                                      int R, int ctx, int beam) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        cur_tok[r] = prompt[Pm];
+        if (idx0) {
+            const int phys = (r / beam) * beam;
+            for (int p = 0; p < Pm; ++p) { idx0[(int64_t)r * ctx + p] = phys; idx1[(int64_t)r * ctx + p] = phys; }
+        }
+    }
+    if (threadIdx.x == 0) { ctl->pos = Pm; ctl->step = Pm; }
+}
+
+mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st) {
+    const mw_model_config& c = m->cfg;
+    DecoderState* s = m->dec;
+    const int d = c.d_model, ctx = c.n_text_ctx, T = c.n_audio_ctx, M = B * Pm, R = B * beam;
+    mw_status r;
+    embed_prefill_kernel<<<M, 128, 0, st>>>(s->prompt, (const __nv_bfloat16*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), m->x, Pm, d);
+    MW_LAUNCH_CHECK();
+    auto gemm = [&](const void* A, int K, const void* W, const float* bias, const float* res, void* out, int N, bool gelu, bool f32) {
+        GemmArgs a;
+        a.a = A; a.a_row_stride = K; a.w = W; a.w_row_stride = K; a.bias = bias;
+        a.residual = res; a.ld_res = N; a.out = out; a.ld_out = N; a.M = M; a.N = N; a.K = K; a.gelu = gelu; a.out_f32 = f32;
+        return gemm_launch(a, st);
+    };
+    for (int l = 0; l < c.dec_layers; ++l) {
+        auto W = [&](int id) { return m->dlw(l, id); };
+        auto F = [&](int id) { return (const float*)m->dlw(l, id); };
+        __nv_bfloat16* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
+        __nv_bfloat16* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
+        if ((r = layernorm_launch(m->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), m->ln, M, d, st)) != MW_OK) return r;
+        if ((r = gemm(m->ln, d, W(MW_DL_WQKV), F(MW_DL_BQKV), nullptr, m->qkv, 3 * d, false, false)) != MW_OK) return r;
+        kv_scatter_kernel<<<M, 128, 0, st>>>(m->qkv, kc, vc, Pm, d, ctx, beam);
+        MW_LAUNCH_CHECK();
+        {   // causal self-attention straight from the packed q|k|v rows of this pass
+            dim3 grid(c.n_heads, M);
+            decode_attn_kernel<false><<<grid, 128, Pm * sizeof(float), st>>>(m->qkv, 3 * d, m->qkv + d, m->qkv + 2 * d, 3 * d, Pm, nullptr,
+                                                                            ctx, s->ctl, Pm, Pm, nullptr, nullptr, 0, m->att, d, Pm);
+            MW_LAUNCH_CHECK();
+        }
+        if ((r = gemm(m->att, d, W(MW_DL_WO), F(MW_DL_BO), m->x, m->x, d, false, true)) != MW_OK) return r;
+        if ((r = layernorm_launch(m->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), m->ln, M, d, st)) != MW_OK) return r;
+        if ((r = gemm(m->ln, d, W(MW_DL_WXQ), F(MW_DL_BXQ), nullptr, m->att, d, false, false)) != MW_OK) return r;     // cross q
+        {
+            __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
+            if ((r = attention_launch_general(m->att, d, 0, kv, 2 * d, 0, d, m->ln, d, B, Pm, T, c.n_heads, st)) != MW_OK) return r;
+        }
+        if ((r = gemm(m->ln, d, W(MW_DL_WXO), F(MW_DL_BXO), m->x, m->x, d, false, true)) != MW_OK) return r;
+        if ((r = layernorm_launch(m->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), m->ln, M, d, st)) != MW_OK) return r;
+        if ((r = gemm(m->ln, d, W(MW_DL_W1), F(MW_DL_B1), nullptr, m->mlp, c.ffn, true, false)) != MW_OK) return r;
+        if ((r = gemm(m->mlp, c.ffn, W(MW_DL_W2), F(MW_DL_B2), m->x, m->x, d, false, true)) != MW_OK) return r;
+    }
+    prefill_finish_kernel<<<1, 256, 0, st>>>(s->prompt, Pm, s->cur_tok, s->ctl, beam > 1 ? s->self_idx[0] : nullptr,
+                                             beam > 1 ? s->self_idx[1] : nullptr, R, ctx, beam);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
 int launches_per_layers(const mw_model_config& c) { return 1 + c.dec_layers * 11; }
 
 mw_status ensure_graphs(mw_model* m, int B, int beam) {
@@ -1270,9 +1355,15 @@ extern "C" mw_status mw_generate(mw_model* m, const void* d_enc, int B, const in
     if ((r = ensure_graphs(m, B, beam)) != MW_OK) return r;
     const int per_prefill = launches_per_layers(c) + 1;
     const int per_gen = launches_per_layers(c) + 2 + (beam > 1 ? 2 : 1);
-    for (int i = 0; i < prompt_len - 1; ++i) {
-        MW_CUDA_CHECK(cudaGraphLaunch(s->graphs.prefill, st));
-        count_launch(per_prefill);
+    const int Pm = prompt_len - 1;
+    const char* force_stepwise = getenv("MW_STEPWISE_PREFILL");      // test hook: compare the two prefill paths
+    if (Pm >= 4 && Pm <= c.n_audio_ctx && !(force_stepwise && force_stepwise[0] == '1')) {
+        if ((r = batched_prefill(m, B, beam, Pm, st)) != MW_OK) return r;       // long prompts (initial_prompt): one pass
+    } else {
+        for (int i = 0; i < Pm; ++i) {
+            MW_CUDA_CHECK(cudaGraphLaunch(s->graphs.prefill, st));
+            count_launch(per_prefill);
+        }
     }
     // generation: the finished counter is polled one window late so the stream never drains
     const int window = 8;
