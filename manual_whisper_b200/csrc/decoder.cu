@@ -423,7 +423,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
 // beam_size times).  Same lane mapping as decode_attn_kernel: 16 bytes per lane, 8 lanes per key.
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
                           const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
                           __nv_bfloat16* __restrict__ out, int ldo) {
@@ -444,9 +444,10 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
     }
     const __nv_bfloat16* kb = kbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
     const __nv_bfloat16* vb = vbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
-    float mx[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) mx[g] = -INFINITY;
+    // Scores: every lane forms 8-dim partial dots for all G queries; a 3-round reduce-scatter over the 8 lanes of a key
+    // (4 + 2 + 1 shuffles instead of 3 per query) leaves lane lg with the complete score of query lg.
+    const bool b2 = lg & 4, b1 = lg & 2, b0 = lg & 1;
+    float mx = -INFINITY;                  // running max of query lg over the keys this lane group sees
     for (int kbase0 = warp * 4; kbase0 < n_keys; kbase0 += 16 * UNR) {
         const int key0 = kbase0 + kq;
         uint4 kv[UNR];
@@ -458,31 +459,43 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int key = key0 + 16 * u;
-            float kf[8];
-            if (key < n_keys) bf16x8_to_float(kv[u], kf);
+            float v[8];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float s = 0.0f;
-                if (key < n_keys) {
+            for (int g = 0; g < 8; ++g) v[g] = 0.0f;
+            if (key < n_keys) {
+                float kf[8];
+                bf16x8_to_float(kv[u], kf);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s = fmaf(qf[g][i], kf[i], s);
+                for (int g = 0; g < G; ++g) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[g] = fmaf(qf[g][i], kf[i], v[g]);
                 }
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                if (key < n_keys) {
-                    if (lg == 0) sc[g * n_keys + key] = s;
-                    mx[g] = fmaxf(mx[g], s);
-                }
+            }
+            float w[4], x2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float send = b2 ? v[i] : v[i + 4];
+                const float keep = b2 ? v[i + 4] : v[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = b1 ? w[i] : w[i + 2];
+                const float keep = b1 ? w[i + 2] : w[i];
+                x2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            const float send = b0 ? x2[0] : x2[1];
+            const float keep = b0 ? x2[1] : x2[0];
+            const float sc_q = keep + __shfl_xor_sync(0xffffffffu, send, 1);      // score of query lg for this key
+            if (key < n_keys && lg < G) {
+                sc[lg * n_keys + key] = sc_q;
+                mx = fmaxf(mx, sc_q);
             }
         }
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
-        if (lane == 0) red_s[g][warp] = mx[g];
-    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    if (kq == 0 && lg < G) red_s[lg][warp] = mx;
     __syncthreads();
 #pragma unroll
     for (int g = 0; g < G; ++g) {
