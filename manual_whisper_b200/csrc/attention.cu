@@ -239,11 +239,8 @@ mw_status attention_launch_general(const void* d_q, int64_t ldq, int colq0, cons
         mw_status s = encode_tensor_map(&tm_kv, d_kv, 3, dims, str, box, true);
         if (s != MW_OK) return s;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        MW_CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM); }));
     dim3 grid(ceil_div(Tq, TQ), n_heads, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;   // d_head^-0.5 * log2(e)
     attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, Tq, Tk, colq0, colk0, colv0, out_ld,

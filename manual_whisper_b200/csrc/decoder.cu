@@ -563,11 +563,8 @@ template <int G>
 mw_status launch_cross_grouped(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int64_t key_stride,
                                int n_keys, __nv_bfloat16* out, int ldo, int n_heads, int B, cudaStream_t st) {
     const size_t smem = (size_t)G * n_keys * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MW_CUDA_CHECK(cudaFuncSetAttribute(cross_attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(cross_attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }));
     MW_REQUIRE(smem <= 96 * 1024, "cross attention: %zu bytes of scores exceed shared memory", smem);
     cross_attn_grouped_kernel<G><<<dim3(n_heads, B), 128, smem, st>>>(q, ldq, k, v, key_stride, n_keys, out, ldo);
     MW_LAUNCH_CHECK();

@@ -264,12 +264,9 @@ EncodeTiledFn get_encode_fn() {
 template <int BLOCK_N, int STAGES>
 mw_status launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N, STAGES>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, STAGES>;
-    if (!attr_set) {
-        MW_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
-    }
+    MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); }));
     const int tiles = p.batch * ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
     kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tw, p);
@@ -280,12 +277,14 @@ mw_status launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const GemmPar
 }  // namespace
 
 int device_sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load();
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev & 63].store(n);
     }
     return n;
 }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <atomic>
+#include <mutex>
 
 #include "../../include/mw_b200.h"
 
@@ -51,6 +52,24 @@ struct DeviceGuard {
     } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute is per device and must have completed before ANY thread launches the kernel there
+// (several host threads drive replicas concurrently): a mutex-guarded per-device flag.
+struct PerDeviceOnce {
+    std::mutex mu;
+    bool done[64] = {};
+    template <typename Fn>
+    cudaError_t run(Fn&& fn) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[dev]) return cudaSuccess;
+        cudaError_t e = fn();
+        if (e == cudaSuccess) done[dev] = true;
+        return e;
+    }
+};
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace mw

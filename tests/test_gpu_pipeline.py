@@ -127,3 +127,16 @@ def test_device_side_vad_front_end(setup):
                           dims=dims, tokens=tok, max_batch=4, vad_method="energy_gpu", streams_per_device=1)
     r1, r2 = p_host.transcribe(a, batch_size=4), p_dev.transcribe(a, batch_size=4)
     assert [(s["start"], s["end"], s["tokens"]) for s in r1["segments"]] == [(s["start"], s["end"], s["tokens"]) for s in r2["segments"]]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_in_process_multi_gpu_replicas(setup):
+    """device_index=[0, 1]: one replica set per GPU in one process; batches are dealt out dynamically, order restored."""
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    two = mw.load_model("tiny", "cuda", device_index=[0, 1], compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+                        vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=2)
+    assert sorted({r.device.index for r in two.replicas}) == [0, 1] and len(two.replicas) == 4
+    a = pipe.transcribe(audio, batch_size=2)
+    b = two.transcribe(audio, batch_size=2)
+    assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
+    assert [(s["start"], s["end"]) for s in a["segments"]] == [(s["start"], s["end"]) for s in b["segments"]]
