@@ -418,6 +418,104 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Greedy cross-attention (the dominant kernel of the decode step): one CTA per (head, row) streams the chunk's K and
+// V exactly once, in a SINGLE pass: every 8-lane group keeps its own online-softmax state (running max, sum and an
+// 8-dim slice of the output) over the keys it owns, so K and V loads are interleaved with no mid-kernel barrier and
+// no score buffer; the 16 partial states of the CTA are merged at the end (log-sum-exp).  Same lane mapping as
+// decode_attn_kernel: 16 bytes per lane, 8 lanes per key, 4 keys per warp instruction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
+                         const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
+                         __nv_bfloat16* __restrict__ out, int ldo) {
+    __shared__ float part_acc[16][64];
+    __shared__ float part_m[16], part_l[16];
+    constexpr int UNR = 4;
+    const int h = blockIdx.x, r = blockIdx.y;
+    const int key_lo = 0, key_hi = n_keys;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lg = lane & 7, kq = lane >> 3;
+    const __nv_bfloat16* kp = kbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
+    const __nv_bfloat16* vp = vbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
+    float qf[8];
+    {
+        const uint4 u = *reinterpret_cast<const uint4*>(q + (int64_t)r * ldq + h * 64 + lg * 8);
+        bf16x8_to_float(u, qf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qf[i] *= 0.125f;
+    }
+    float m = -INFINITY, l = 0.0f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int kbase0 = key_lo + warp * 4; kbase0 < key_hi; kbase0 += 16 * UNR) {   // warp-uniform trip count (shuffles inside)
+        const int key0 = kbase0 + kq;
+        uint4 kv[UNR], vv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int key = key0 + 16 * u;
+            if (key < key_hi) {
+                kv[u] = *reinterpret_cast<const uint4*>(kp + (int64_t)key * key_stride);
+                vv[u] = *reinterpret_cast<const uint4*>(vp + (int64_t)key * key_stride);
+            }
+        }
+        float sv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            sv[u] = 0.0f;
+            if (key0 + 16 * u < key_hi) {
+                float kf[8];
+                bf16x8_to_float(kv[u], kf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sv[u] = fmaf(qf[i], kf[i], sv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            sv[u] += __shfl_xor_sync(0xffffffffu, sv[u], 1);
+            sv[u] += __shfl_xor_sync(0xffffffffu, sv[u], 2);
+            sv[u] += __shfl_xor_sync(0xffffffffu, sv[u], 4);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (key0 + 16 * u < key_hi) {
+                const float sc = sv[u];
+                if (sc > m) {                       // uniform over the 8 lanes of the key; rare after the first keys
+                    const float scale = __expf(m - sc);      // exp(-inf) = 0 on the first key
+                    l *= scale;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] *= scale;
+                    m = sc;
+                }
+                const float p = __expf(sc - m);
+                l += p;
+                float vf[8];
+                bf16x8_to_float(vv[u], vf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+            }
+        }
+    }
+    const int grp = warp * 4 + kq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part_acc[grp][lg * 8 + i] = acc[i];
+    if (lg == 0) { part_m[grp] = m; part_l[grp] = l; }
+    __syncthreads();
+    if (tid < 64) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) M = fmaxf(M, part_m[g]);
+        float num = 0.0f, den = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            const float w = (part_m[g] == -INFINITY) ? 0.0f : __expf(part_m[g] - M);     // groups that saw no key
+            num = fmaf(w, part_acc[g][tid], num);
+            den = fmaf(w, part_l[g], den);
+        }
+        out[(int64_t)r * ldo + h * 64 + tid] = __float2bfloat16(num / den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Grouped cross-attention for beam search: the G hypotheses of one chunk attend to the SAME encoder K/V, so one CTA
 // per (head, chunk) streams K and V once and serves all G queries (CTranslate2 instead tiles the encoder output
 // beam_size times).  Same lane mapping as decode_attn_kernel: 16 bytes per lane, 8 lanes per key.
@@ -1087,8 +1185,7 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                 if (r != MW_OK) return r;
             } else {
                 dim3 grid(c.n_heads, R);
-                decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(
-                    s->qx, d, kv, kv + d, 2 * d, T, nullptr, ctx, s->ctl, T, beam, nullptr, nullptr, 0, s->att, d);
+                cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
                 MW_LAUNCH_CHECK();
             }
         }
@@ -1525,8 +1622,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
         if (which == 0) {
             __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             dim3 grid(c.n_heads, B);
-            decode_attn_kernel<false><<<grid, 128, T * sizeof(float), st>>>(s->qx, d, kv, kv + d, 2 * d, T, nullptr, c.n_text_ctx,
-                                                                           s->ctl, T, 1, nullptr, nullptr, 0, s->att, d);
+            cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
             MW_LAUNCH_CHECK();
             return MW_OK;
         }
