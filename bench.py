@@ -294,7 +294,7 @@ def main():
         eng = model.engine
         d, T = dims.d_model, dims.n_audio_ctx
         cand = [
-            ("decode_attn_kernel<cross>", 0, BATCH * T * 2 * d * 2, dims.dec_layers * 224),
+            ("cross_attn_stream_kernel", 0, BATCH * T * 2 * d * 2, dims.dec_layers * 224),
             ("skinny_gemm_kernel(fc1)", 1, dims.ffn * d * 2, 2 * dims.dec_layers * 224),      # fc1 + fc2 (same bytes)
             ("skinny_gemm_kernel(d x d)", 2, d * d * 2, 4 * dims.dec_layers * 224),           # q-k-v counted as 3 more below
         ]
@@ -306,7 +306,7 @@ def main():
         dom = max(kern, key=lambda k: k["share_of_step"])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
         # (profiles/ncu_decode_attn_r1.txt); only the cross-attention kernel has been captured so far
-        traffic = 245.87e6 + 4.65e6 if dom["kernel"].startswith("decode_attn") else None
+        traffic = 245.87e6 + 4.65e6 if dom["kernel"].startswith("cross_attn") else None
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": hbm, "unit": "GB/s",
                     "frac": dom["GBps"] / hbm, "traffic": traffic, "peak_source": which_peak,
                     "all": kern}

@@ -297,7 +297,11 @@ class FasterWhisperPipeline:
         replicas (one host thread + one stream each); results come back in window order."""
         options = options or self.options
         n = len(offs)
-        batches = [(i, min(i + batch_size, n)) for i in range(0, n, batch_size)]
+        # ceil(n / batch_size) batches as upstream, but of even size (28,27,27,27,27 instead of 32,32,32,32,8): rows are
+        # independent, so results are unchanged, and no replica is left with a latency-bound stub batch at the end
+        n_b = max(1, -(-n // batch_size))
+        edges = [round(i * n / n_b) for i in range(n_b + 1)]
+        batches = [(edges[i], edges[i + 1]) for i in range(n_b) if edges[i + 1] > edges[i]]
         if batch_order is not None:
             batches = [batches[i] for i in batch_order]
         out: List = [None] * n

@@ -79,8 +79,13 @@ struct DecoderState {
     mw::DecCtl* h_ctl = nullptr;         // pinned [2]
     cudaStream_t cap_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    struct Graphs { int R = 0, beam = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
-    Graphs graphs;
+    // step graphs are specific to (rows, beam): a small cache keeps the last few shapes (full batches and the short
+    // last batch of a recording alternate) so they are not re-captured on every call
+    struct Graphs { int R = 0, beam = 0; uint64_t last_use = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
+    static constexpr int GRAPH_CACHE = 4;
+    Graphs graph_cache[GRAPH_CACHE];
+    uint64_t graph_clock = 0;
+    Graphs graphs;                       // the entry selected by ensure_graphs for the current call (non-owning copy)
 };
 
 namespace mw {
@@ -1107,9 +1112,13 @@ mw_status decoder_state_create(mw_model* m) {
     return MW_OK;
 }
 
+static void destroy_graph_entry(DecoderState::Graphs& g) {
+    if (g.prefill) cudaGraphExecDestroy(g.prefill);
+    for (int i = 0; i < 2; ++i) if (g.gen[i]) cudaGraphExecDestroy(g.gen[i]);
+    g = DecoderState::Graphs();
+}
 static void destroy_graphs(DecoderState* s) {
-    if (s->graphs.prefill) cudaGraphExecDestroy(s->graphs.prefill);
-    for (int i = 0; i < 2; ++i) if (s->graphs.gen[i]) cudaGraphExecDestroy(s->graphs.gen[i]);
+    for (auto& g : s->graph_cache) destroy_graph_entry(g);
     s->graphs = DecoderState::Graphs();
 }
 
@@ -1331,8 +1340,16 @@ int launches_per_layers(const mw_model_config& c) { return 1 + c.dec_layers * 11
 mw_status ensure_graphs(mw_model* m, int B, int beam) {
     DecoderState* s = m->dec;
     const int R = B * beam;
-    if (s->graphs.R == R && s->graphs.beam == beam && s->graphs.prefill) return MW_OK;
-    destroy_graphs(s);
+    DecoderState::Graphs* slot = nullptr;
+    for (auto& g : s->graph_cache)
+        if (g.prefill && g.R == R && g.beam == beam) { g.last_use = ++s->graph_clock; s->graphs = g; return MW_OK; }
+    slot = &s->graph_cache[0];                // a free slot, else the least recently used one
+    for (auto& g : s->graph_cache) {
+        if (!g.prefill) { slot = &g; break; }
+        if (g.last_use < slot->last_use) slot = &g;
+    }
+    destroy_graph_entry(*slot);
+    s->graphs = DecoderState::Graphs();
     mw_status r;
     // prefill step: layers + forced advance.  With beam search the prefill rows are their own ancestors, so the
     // identity index table (phase 0) is used.
@@ -1343,7 +1360,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
         MW_LAUNCH_CHECK();
         return MW_OK;
     });
-    if (r != MW_OK) return r;
+    if (r != MW_OK) { destroy_graph_entry(s->graphs); return r; }
     for (int phase = 0; phase < (beam > 1 ? 2 : 1); ++phase) {
         r = capture_graph(s, &s->graphs.gen[phase], [&](cudaStream_t st) -> mw_status {
             mw_status q = enqueue_layers(m, R, beam, phase, st);
@@ -1351,10 +1368,12 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
             if ((q = enqueue_logits(m, R, st)) != MW_OK) return q;
             return enqueue_select(m, B, beam, phase, st);
         });
-        if (r != MW_OK) return r;
+        if (r != MW_OK) { destroy_graph_entry(s->graphs); return r; }
     }
     s->graphs.R = R;
     s->graphs.beam = beam;
+    s->graphs.last_use = ++s->graph_clock;
+    *slot = s->graphs;
     return MW_OK;
 }
 
