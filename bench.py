@@ -305,8 +305,8 @@ def main():
                          "launches_per_step": per_step, "share_of_step": kms * per_step / (ms_max / args.steps)})
         dom = max(kern, key=lambda k: k["share_of_step"])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-        # (profiles/ncu_decode_attn_r1.txt); only the cross-attention kernel has been captured so far
-        traffic = 245.87e6 + 4.65e6 if dom["kernel"].startswith("cross_attn") else None
+        # (profiles/ncu_cross_attn_r1.txt); only the cross-attention kernel has been captured so far
+        traffic = 245.86e6 + 3.67e6 if dom["kernel"].startswith("cross_attn") else None
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": hbm, "unit": "GB/s",
                     "frac": dom["GBps"] / hbm, "traffic": traffic, "peak_source": which_peak,
                     "all": kern}
