@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Flagship-size parity (BASELINE.json configs[1] generalised to a few windows): Whisper large-v3, the SAME seeded
+"""Parity at scale (usage: parity_large_v3.py N_WINDOWS MAX_LENGTH SCHEME [MODEL]).
+Flagship-size parity (BASELINE.json configs[1] generalised to a few windows): Whisper large-v3, the SAME seeded
 random-init weights (rounded to bf16 once) on both sides, greedy decoding of VAD windows of the synthetic recording:
    * log-mel: max abs error vs the oracle (tolerance 1e-4)
    * encoder output: relative L2 vs the fp32 oracle
@@ -19,12 +20,13 @@ from oracle.generate import generate, GenOptions
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 MAXLEN = int(sys.argv[2]) if len(sys.argv) > 2 else 448
 scheme = sys.argv[3] if len(sys.argv) > 3 else "survey"
-dims = model_dims("large-v3"); tok = special_tokens(dims.vocab)
+MODEL = sys.argv[4] if len(sys.argv) > 4 else "large-v3"
+dims = model_dims(MODEL); tok = special_tokens(dims.vocab)
 t0 = time.time(); sd = random_init(dims, seed=1234, scheme=scheme); t_init = time.time() - t0
 audio, turns = mw.synthetic_speech(N * 30.0 + 5, seed=1)
 wins = mw.merge_chunks(turns, 30)[:N]
 offs = [int(w["start"] * 16000) for w in wins]; lens = [int(w["end"] * 16000) - o for w, o in zip(wins, offs)]
-pipe = mw.load_model("large-v3", "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1}, model=sd,
+pipe = mw.load_model(MODEL, "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1}, model=sd,
                      vad_model=mw.InjectedVad([(w["start"], w["end"]) for w in wins]), max_batch=max(N, 1), streams_per_device=1)
 model = pipe.model
 model.max_length = MAXLEN
@@ -34,7 +36,7 @@ d_audio = torch.from_numpy(audio).cuda()
 mel_gpu = model.plan.chunks(d_audio, torch.tensor(offs).cuda(), torch.tensor(lens, dtype=torch.int32).cuda()).cpu()
 mel = log_mel_chunks(audio, offs, lens, dims.n_mels)
 enc_gpu = model.engine.encode(mel_gpu.cuda()).float().cpu()
-out = {"model": "large-v3", "windows": N, "max_length": MAXLEN, "init_scheme": scheme, "weights_init_s": t_init,
+out = {"model": MODEL, "windows": N, "max_length": MAXLEN, "init_scheme": scheme, "weights_init_s": t_init,
        "logmel_max_abs_err": float((mel_gpu - mel).abs().max())}
 prompt = [tok.sot, tok.lang_id("zh"), tok.transcribe, tok.no_timestamps]
 torch.set_num_threads(os.cpu_count() or 8)
@@ -75,6 +77,10 @@ for name, emu in (("fp32", False), ("bf16_rounding", True)):
                 worst = max(worst, float(top[0] - top[1]))
     out[f"teacher_forced_vs_{name}"] = {"steps": total, "argmax_agree": agree, "fraction": agree / max(total, 1),
                                       "largest_oracle_margin_among_disagreements": worst}
-    out[f"greedy_vs_{name}"] = {"identical": sum(r["identical"] for r in rows), "of": N, "rows": rows, "oracle_seconds": time.time() - t0,
+    div = [r for r in rows if not r["identical"]]
+    out[f"greedy_vs_{name}"] = {"identical": sum(r["identical"] for r in rows), "of": N,
+                               "mean_common_prefix": float(np.mean([r["len"] if r["identical"] else r["first_divergence"] for r in rows])),
+                               "largest_margin_at_first_divergence": max([r["oracle_top2_margin"] for r in div], default=0.0),
+                               "rows": rows if N <= 8 else div[:16], "oracle_seconds": time.time() - t0,
                                "unique_ids_window0": len(set(ref[0].sequences_ids[0]))}
 print(json.dumps(out, indent=1))

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-NEAR_TIE = 0.05
+NEAR_TIE = 0.03
 
 
 @pytest.fixture(scope="module")
