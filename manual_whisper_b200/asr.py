@@ -375,8 +375,9 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
     reference sets DEVICE="cpu" (/root/reference/transcribe.py:30) and tells GPU users to change that
     constant (/root/reference/README.md:101) — there is no CPU path here.  ``compute_type`` is accepted for
     signature parity; the engine always computes in bf16 with fp32 accumulation.  ``model`` may be a ready
-    WhisperModel or an HF-named state dict; with neither, seeded random-init weights are used because no
-    checkpoint can be downloaded offline (a warning says so).  Keyword-only arguments are additions;
+    WhisperModel, an HF-named state dict, or the path of a Hugging Face ``model.safetensors`` (also looked up under
+    ``download_root``); with none of these, seeded random-init weights are used because no checkpoint can be downloaded
+    offline (a warning says so).  Keyword-only arguments are additions;
     ``streams_per_device`` replicas per GPU share one copy of the weights and keep that many batches in flight.
     """
     if whisper_arch.endswith(".en"):
@@ -406,8 +407,21 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
     if isinstance(model, WhisperModel):
         replicas = [model]
     else:
+        ckpt = model if isinstance(model, str) else None
+        if ckpt is None and download_root:
+            import os
+            for cand in (os.path.join(download_root, whisper_arch, "model.safetensors"), os.path.join(download_root, "model.safetensors")):
+                if os.path.exists(cand):
+                    ckpt = cand
+                    break
         if isinstance(model, dict):
             sd = model
+        elif ckpt is not None:
+            # a Hugging Face Whisper checkpoint (keys of WhisperForConditionalGeneration.state_dict()), e.g. openai/whisper-large-v3
+            from safetensors.torch import load_file
+            sd = load_file(ckpt)
+            if "model.encoder.embed_positions.weight" not in sd:
+                raise ValueError(f"{ckpt} is not a Hugging Face Whisper checkpoint (missing model.encoder.* keys)")
         else:
             warnings.warn(f"no '{whisper_arch}' checkpoint is reachable offline: using seeded random-init weights "
                           f"(scheme={init_scheme!r}, seed={init_seed}); transcripts are token ids, not text")

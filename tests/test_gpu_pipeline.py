@@ -140,3 +140,19 @@ def test_in_process_multi_gpu_replicas(setup):
     b = two.transcribe(audio, batch_size=2)
     assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
     assert [(s["start"], s["end"]) for s in a["segments"]] == [(s["start"], s["end"]) for s in b["segments"]]
+
+
+def test_load_model_from_safetensors_checkpoint(setup, tmp_path):
+    """A Hugging Face ``model.safetensors`` path (or one under download_root) loads to the same engine as its state dict."""
+    from safetensors.torch import save_file
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    path = tmp_path / "tiny" / "model.safetensors"
+    path.parent.mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(path))
+    kw = dict(compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), dims=dims,
+              tokens=tok, max_batch=4)
+    by_path = mw.load_model("tiny", "cuda", model=str(path), **kw)
+    by_root = mw.load_model("tiny", "cuda", download_root=str(tmp_path), **kw)
+    want = [s["tokens"] for s in pipe.transcribe(audio, batch_size=4)["segments"]]
+    assert [s["tokens"] for s in by_path.transcribe(audio, batch_size=4)["segments"]] == want
+    assert [s["tokens"] for s in by_root.transcribe(audio, batch_size=4)["segments"]] == want

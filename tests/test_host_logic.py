@@ -138,3 +138,11 @@ def test_shim_exposes_the_names_transcribe_py_uses():
     finally:
         sys.path.remove(shim)
         sys.modules.pop("whisperx", None)
+
+
+def test_load_model_rejects_non_whisper_checkpoint(tmp_path):
+    from safetensors.torch import save_file
+    bad = str(tmp_path / "model.safetensors")
+    save_file({"foo": torch.zeros(2)}, bad)
+    with pytest.raises(ValueError, match="not a Hugging Face Whisper checkpoint"):
+        mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", model=bad)
