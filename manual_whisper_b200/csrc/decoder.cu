@@ -526,7 +526,7 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
 // beam_size times).  Same lane mapping as decode_attn_kernel: 16 bytes per lane, 8 lanes per key.
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
                           const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
                           __nv_bfloat16* __restrict__ out, int ldo) {
@@ -1630,7 +1630,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
     MW_REQUIRE(m && h_ms_avg && iters > 0, "mw_bench_kernel: bad argument");
     const mw_model_config& c = m->cfg;
     DecoderState* s = m->dec;
-    MW_REQUIRE(B > 0 && B <= c.max_batch, "mw_bench_kernel: B outside 1..max_batch");
+    MW_REQUIRE(B > 0 && B <= c.max_batch * (which == 0 ? 1 : c.max_beam), "mw_bench_kernel: B outside 1..max_batch (x max_beam for the GEMMs)");
     mw::DeviceGuard guard(c.device);
     cudaStream_t st = (cudaStream_t)stream;
     const int d = c.d_model, T = c.n_audio_ctx;
