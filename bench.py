@@ -7,7 +7,7 @@ generator and merged into <=30 s windows, batch_size=32, greedy decoding, random
 owns its own recording (weak scaling, no data-path collective).
 
   step   = one batch of 32 windows through log-mel -> encoder -> greedy decode (224 tokens: random-init
-           weights never emit <eot>, so every window decodes to the cap — worst case).  --streams batches (default 4)
+           weights never emit <eot>, so every window decodes to the cap — worst case).  --streams batches (default 8)
            are kept in flight per GPU (shared-weight replicas, one stream each) so one batch's launch gaps are
            filled by the others' kernels; ms_per_step = timed region / K.
   value  = audio seconds of the windows processed in the K timed steps / device time, inputs resident in HBM.
@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-repeats", type=int, default=1)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: do not time the public-API pass")
-    ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (shared-weight replicas)")
+    ap.add_argument("--streams", type=int, default=8, help="batches in flight per GPU (shared-weight replicas)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
