@@ -1,0 +1,78 @@
+"""wav2vec2-CTC alignment model: dimensions, Hugging Face checkpoint key names and seeded random-init weights.
+
+The reference aligns with ``whisperx.load_align_model(language_code, device)`` (/root/reference/transcribe.py:127-129); for
+"zh" that is a Hugging Face ``Wav2Vec2ForCTC`` of the XLSR-53 family (feat_extract_norm="layer", do_stable_layer_norm=True),
+which is the variant the CUDA engine implements (csrc/w2v.cu).  No checkpoint exists offline, so `random_init_w2v` provides
+seeded weights of that architecture for tests and benchmarks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class W2vDims:
+    name: str = "w2v-large-xlsr"
+    n_layers: int = 24
+    d_model: int = 1024
+    n_heads: int = 16
+    ffn: int = 4096
+    vocab: int = 32
+    conv_dim: int = 512
+    conv_kernel: Tuple[int, ...] = (10, 3, 3, 3, 3, 2, 2)
+    conv_stride: Tuple[int, ...] = (5, 2, 2, 2, 2, 2, 2)
+    pos_kernel: int = 128
+    pos_groups: int = 16
+
+    def frames(self, n_samples: int) -> int:
+        t = int(n_samples)
+        for k, s in zip(self.conv_kernel, self.conv_stride):
+            t = (t - k) // s + 1 if t >= k else 0
+        return max(t, 0)
+
+
+
+def random_init_w2v(dims: W2vDims, seed: int = 0, std: float = 0.05) -> Dict[str, torch.Tensor]:
+    """Seeded random-init weights with the Hugging Face ``Wav2Vec2ForCTC`` key names; every matrix is bf16-representable so
+    the CUDA engine and this oracle hold identical values.  The positional conv is stored as its effective weight."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rnd(*shape, s=std):
+        return (torch.randn(*shape, generator=g) * s).to(torch.bfloat16).to(torch.float32)
+
+    sd: Dict[str, torch.Tensor] = {}
+    c_in = 1
+    for i, k in enumerate(dims.conv_kernel):
+        p = f"wav2vec2.feature_extractor.conv_layers.{i}"
+        sd[p + ".conv.weight"] = rnd(dims.conv_dim, c_in, k, s=(2.0 / (c_in * k)) ** 0.5)
+        sd[p + ".conv.bias"] = rnd(dims.conv_dim, s=0.02)
+        sd[p + ".layer_norm.weight"] = 1.0 + rnd(dims.conv_dim, s=0.05)
+        sd[p + ".layer_norm.bias"] = rnd(dims.conv_dim, s=0.05)
+        c_in = dims.conv_dim
+    sd["wav2vec2.feature_projection.layer_norm.weight"] = 1.0 + rnd(dims.conv_dim, s=0.05)
+    sd["wav2vec2.feature_projection.layer_norm.bias"] = rnd(dims.conv_dim, s=0.05)
+    sd["wav2vec2.feature_projection.projection.weight"] = rnd(dims.d_model, dims.conv_dim)
+    sd["wav2vec2.feature_projection.projection.bias"] = rnd(dims.d_model, s=0.02)
+    gs = dims.d_model // dims.pos_groups
+    sd["wav2vec2.encoder.pos_conv_embed.conv.weight"] = rnd(dims.d_model, gs, dims.pos_kernel, s=(1.0 / (gs * dims.pos_kernel)) ** 0.5)
+    sd["wav2vec2.encoder.pos_conv_embed.conv.bias"] = rnd(dims.d_model, s=0.02)
+    for l in range(dims.n_layers):
+        p = f"wav2vec2.encoder.layers.{l}"
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[f"{p}.attention.{nm}.weight"] = rnd(dims.d_model, dims.d_model)
+            sd[f"{p}.attention.{nm}.bias"] = rnd(dims.d_model, s=0.02)
+        for nm in ("layer_norm", "final_layer_norm"):
+            sd[f"{p}.{nm}.weight"] = 1.0 + rnd(dims.d_model, s=0.05)
+            sd[f"{p}.{nm}.bias"] = rnd(dims.d_model, s=0.05)
+        sd[p + ".feed_forward.intermediate_dense.weight"] = rnd(dims.ffn, dims.d_model)
+        sd[p + ".feed_forward.intermediate_dense.bias"] = rnd(dims.ffn, s=0.02)
+        sd[p + ".feed_forward.output_dense.weight"] = rnd(dims.d_model, dims.ffn, s=std / 2)
+        sd[p + ".feed_forward.output_dense.bias"] = rnd(dims.d_model, s=0.02)
+    sd["wav2vec2.encoder.layer_norm.weight"] = 1.0 + rnd(dims.d_model, s=0.05)
+    sd["wav2vec2.encoder.layer_norm.bias"] = rnd(dims.d_model, s=0.05)
+    sd["lm_head.weight"] = rnd(dims.vocab, dims.d_model, s=0.2)
+    sd["lm_head.bias"] = rnd(dims.vocab, s=0.02)
+    return sd
