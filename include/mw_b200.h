@@ -191,6 +191,65 @@ mw_status mw_bench_kernel(mw_model* model, int which, int B, int iters, float* h
  * 1 embed, 2 LayerNorm, 4 skinny GEMMs, 8 self-attention, 16 cross-attention, 32 final LN + logits GEMM. */
 mw_status mw_bench_step(mw_model* model, int B, int parts, int iters, float* h_ms_avg, void* stream);
 
+/* ------------------------------------------------------------------ forced alignment ------
+ * Replaces what whisperx.align runs per segment (/root/reference/transcribe.py:127-135): the wav2vec2-CTC acoustic
+ * model (Hugging Face Wav2Vec2ForCTC, feat_extract_norm="layer", do_stable_layer_norm=True - the XLSR-53 family
+ * whisperx loads for "zh") -> log_softmax emissions, and the CTC trellis + backtrack of whisperx/alignment.py.
+ * Windows of different lengths are batched: every per-frame op is row-wise, the positional conv sees zeros beyond a
+ * window's last frame and self-attention masks keys beyond it, so each window's emissions equal a solo run. */
+typedef struct mw_w2v mw_w2v;
+
+typedef struct mw_w2v_config {
+    int32_t n_layers, d_model, n_heads, ffn;
+    int32_t vocab;           /* real CTC vocabulary; lm_head rows are padded to a multiple of 32 by the host */
+    int32_t conv_dim;        /* 512: channels of the 7 feature-extractor convs (kernels 10,3,3,3,3,2,2; strides 5,2,2,2,2,2,2) */
+    int32_t pos_kernel;      /* 128 */
+    int32_t pos_groups;      /* 16; d_model / pos_groups must be 64 */
+    int32_t max_batch;       /* windows per mw_w2v_emissions call */
+    int32_t max_samples;     /* longest window in samples (480000 = 30 s) */
+    int32_t device;
+} mw_w2v_config;
+
+/* Weight table: MW_A_* globals, then n_layers blocks in the order of enum mw_enc_layer_weight_id (q|k|v rows
+ * concatenated, all three biases real).  Matrices bf16 row-major [out, in]; vectors fp32; pointers borrowed. */
+enum mw_w2v_weight_id {
+    MW_A_CONV0_W = 0,     /* f32 [conv_dim, 10] */
+    MW_A_CONV0_B, MW_A_CONV0_LN_G, MW_A_CONV0_LN_B,
+    MW_A_CONV1_W,         /* conv layer i = 1..6 at MW_A_CONV0_W + 4 i: bf16 [conv_dim, k_i * conv_dim] as [co][tap][ci], */
+    MW_A_CONV1_B, MW_A_CONV1_LN_G, MW_A_CONV1_LN_B,   /* then bias, LayerNorm gamma, beta */
+    MW_A_FP_LN_G = 28, MW_A_FP_LN_B,   /* feature_projection.layer_norm */
+    MW_A_FP_W, MW_A_FP_B,              /* feature_projection.projection: bf16 [d, conv_dim], f32 [d] */
+    MW_A_POS_W,           /* bf16 [groups][64 out][pos_kernel taps][64 in]: effective (weight-normalised) pos-conv weight */
+    MW_A_POS_B,           /* f32 [d] */
+    MW_A_ENC_LN_G, MW_A_ENC_LN_B,      /* encoder.layer_norm (after the last layer) */
+    MW_A_LM_W, MW_A_LM_B,              /* lm_head: bf16 [ceil32(vocab), d], f32 [ceil32(vocab)] */
+    MW_A_GLOBAL_COUNT
+};
+
+mw_status mw_w2v_create(const mw_w2v_config* cfg, const mw_weight_table* weights, mw_w2v** out_model);
+void mw_w2v_destroy(mw_w2v* model);
+int64_t mw_w2v_workspace_bytes(const mw_w2v* model);
+/* frames the conv stack yields for n_samples (0 below 400 samples) */
+int32_t mw_w2v_frames(int64_t n_samples);
+
+/* Emissions of n windows: window c = d_audio[d_offsets[c] .. + d_lengths[c]), shorter than 400 samples is zero-padded to
+ * 400 as whisperx does.  h_lengths: host copy of the lengths (sizes the launch).  d_out: f32, window c at
+ * d_out + c * out_window_stride, [frames_c, vocab] log-probabilities (rows beyond frames_c are not written);
+ * out_window_stride >= mw_w2v_frames(max length) * vocab. */
+mw_status mw_w2v_emissions(mw_w2v* model, const float* d_audio, int64_t n_audio, const int64_t* d_offsets,
+                           const int32_t* d_lengths, const int32_t* h_lengths, int n, float* d_out,
+                           int64_t out_window_stride, void* stream);
+
+/* CTC forced alignment of n windows (whisperx get_trellis + backtrack).  Emissions as written by mw_w2v_emissions;
+ * d_frames[c] = valid frames; d_tokens [n, max_tokens] dictionary ids (-1 = wildcard: best non-blank symbol),
+ * d_n_tokens[c] of them used.  Outputs per frame: d_frame_token [n, max_frames] = index into the window's token list,
+ * d_frame_score [n, max_frames] = probability of the symbol the path emitted there; d_ok[c] = 0 when the window is not
+ * alignable (more tokens than frames, or no tokens).  d_workspace: f32 [n * max_frames * (max_tokens + 1)] scratch. */
+mw_status mw_ctc_align(const float* d_emissions, int64_t window_stride, int vocab, const int32_t* d_frames,
+                       const int32_t* d_tokens, int max_tokens, const int32_t* d_n_tokens, int n, int blank,
+                       int32_t* d_frame_token, float* d_frame_score, int max_frames, int32_t* d_ok,
+                       float* d_workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

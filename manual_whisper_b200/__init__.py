@@ -11,9 +11,12 @@ from .audio import load_audio, log_mel_spectrogram, pad_or_trim, mel_filters
 from .asr import load_model, FasterWhisperPipeline, WhisperModel, TranscriptionOptions, get_prompt
 from .vad import merge_chunks, InjectedVad, EnergyVad, GpuEnergyVad, synthetic_speech
 from .tokenizer import Tokenizer
+from .alignment import load_align_model, align, AlignModel, AlignEngine
+from .w2v import W2vDims, random_init_w2v
 
 __version__ = "0.1.0"
 __all__ = [
+    "load_align_model", "align", "AlignModel", "AlignEngine", "W2vDims", "random_init_w2v",
     "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
     "load_audio", "log_mel_spectrogram", "pad_or_trim", "mel_filters", "load_model", "FasterWhisperPipeline",
     "WhisperModel", "TranscriptionOptions", "get_prompt", "merge_chunks", "InjectedVad", "EnergyVad", "GpuEnergyVad",

@@ -33,6 +33,12 @@ class ModelConfigC(C.Structure):
         "n_audio_ctx", "n_text_ctx", "max_batch", "max_beam", "device")]
 
 
+class W2vConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_layers", "d_model", "n_heads", "ffn", "vocab", "conv_dim", "pos_kernel", "pos_groups", "max_batch", "max_samples",
+        "device")]
+
+
 class WeightTableC(C.Structure):
     _fields_ = [("n", C.c_int32), ("ptrs", C.POINTER(C.c_void_p))]
 
@@ -65,6 +71,14 @@ SIGNATURES = {
     "mw_bench_step": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "mw_frame_rms": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "mw_layernorm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mw_w2v_create": (C.c_int32, [C.POINTER(W2vConfigC), C.POINTER(WeightTableC), C.POINTER(C.c_void_p)]),
+    "mw_w2v_destroy": (None, [C.c_void_p]),
+    "mw_w2v_workspace_bytes": (C.c_int64, [C.c_void_p]),
+    "mw_w2v_frames": (C.c_int32, [C.c_int64]),
+    "mw_w2v_emissions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_i32p, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_void_p]),
+    "mw_ctc_align": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

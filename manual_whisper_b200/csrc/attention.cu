@@ -36,8 +36,8 @@ __device__ __forceinline__ float ex2(float x) {
 // serves the others, which is what hides the MMA / mbarrier / tcgen05.ld latencies of the serial per-block chain.
 __global__ void __launch_bounds__(128, 3)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         __nv_bfloat16* __restrict__ out, int Tq, int Tk, int colq0, int colk0, int colv0, int out_ld,
-                         float scale_log2e) {
+                         __nv_bfloat16* __restrict__ out, int Tq, int Tk_max, int colq0, int colk0, int colv0, int out_ld,
+                         float scale_log2e, const int* __restrict__ kv_lens) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
@@ -55,6 +55,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * TQ;
     const int h = blockIdx.y, b = blockIdx.z;
+    // ragged self-attention (forced-alignment windows of different lengths): keys >= kv_lens[b] are masked exactly like the
+    // tail of the last key block, and query tiles that lie wholly in the padding are skipped
+    const int Tk = kv_lens ? min(Tk_max, max(__ldg(kv_lens + b), 1)) : Tk_max;
+    if (kv_lens && q0 >= Tk) return;
     const int n_blocks = (Tk + TK - 1) / TK;
     const int col_q = colq0 + h * DH, col_k = colk0 + h * DH, col_v = colv0 + h * DH;
 
@@ -222,7 +226,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // colk0 + 64 h / colv0 + 64 h); out [B*Tq, out_ld].  The encoder's self-attention and the decoder's batched-prefill
 // cross-attention are both instances.
 mw_status attention_launch_general(const void* d_q, int64_t ldq, int colq0, const void* d_kv, int64_t ldkv, int colk0, int colv0,
-                                   void* d_out, int out_ld, int B, int Tq, int Tk, int n_heads, cudaStream_t st) {
+                                   void* d_out, int out_ld, int B, int Tq, int Tk, int n_heads, cudaStream_t st,
+                                   const int* d_kv_lens) {
     MW_REQUIRE(d_q && d_kv && d_out && B > 0 && Tq > 0 && Tk > 0 && n_heads > 0, "attention: bad arguments");
     CUtensorMap tm_q, tm_kv;
     {
@@ -244,18 +249,18 @@ mw_status attention_launch_general(const void* d_q, int64_t ldq, int colq0, cons
     dim3 grid(ceil_div(Tq, TQ), n_heads, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;   // d_head^-0.5 * log2(e)
     attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, Tq, Tk, colq0, colk0, colv0, out_ld,
-                                                          scale_log2e);
+                                                          scale_log2e, d_kv_lens);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
 
-mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_heads, cudaStream_t st) {
+mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_heads, cudaStream_t st, const int* d_lens) {
     const int d = n_heads * DH;
-    return attention_launch_general(d_qkv, 3 * d, 0, d_qkv, 3 * d, d, 2 * d, d_out, d, B, T, T, n_heads, st);
+    return attention_launch_general(d_qkv, 3 * d, 0, d_qkv, 3 * d, d, 2 * d, d_out, d, B, T, T, n_heads, st, d_lens);
 }
 
 }  // namespace mw
 
 extern "C" mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream) {
-    return mw::attention_launch(d_qkv, d_out, B, T, n_heads, (cudaStream_t)stream);
+    return mw::attention_launch(d_qkv, d_out, B, T, n_heads, (cudaStream_t)stream, nullptr);
 }

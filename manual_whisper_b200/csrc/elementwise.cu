@@ -7,11 +7,14 @@ namespace mw {
 
 namespace {
 
-// one warp per row; d % 128 == 0, d <= 128 * MAXV
-template <int MAXV>
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+
+// one warp per row; d % 128 == 0, d <= 128 * MAXV.  MODE 0: LN -> bf16; 1: GELU(LN) -> bf16; 2: GELU(LN) -> f32
+template <int MAXV, int MODE = 0>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ out, int rows, int d) {
+                 void* __restrict__ out_v, int rows, int d) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_v);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -45,8 +48,15 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) {
             const float4 g = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+            float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+            float y2 = (v[i].z - mean) * rstd * g.z + bb.z, y3 = (v[i].w - mean) * rstd * g.w + bb.w;
+            if (MODE != 0) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3); }
+            if (MODE == 2) {
+                reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + (int64_t)row * d)[i * 32 + lane] = make_float4(y0, y1, y2, y3);
+                continue;
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(y2, y3);
             uint2 u;
             u.x = *reinterpret_cast<uint32_t*>(&h0);
             u.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -103,9 +113,22 @@ mw_status layernorm_launch(const float* x, const float* gamma, const float* beta
     MW_REQUIRE(d % 128 == 0 && d >= 128 && d <= 2048, "layernorm: d=%d must be a multiple of 128 in [128, 2048]", d);
     if (rows <= 0) return MW_OK;
     const int grid = ceil_div(rows, 8);
-    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
-    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
-    else layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, d);
+    if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
+    else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
+    else layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+mw_status layernorm_act_launch(const float* x, const float* gamma, const float* beta, void* out, int rows, int d, int mode,
+                               cudaStream_t st) {
+    MW_REQUIRE(x && gamma && beta && out, "layernorm_act: null pointer");
+    MW_REQUIRE(d % 128 == 0 && d >= 128 && d <= 512, "layernorm_act: d=%d must be a multiple of 128 in [128, 512]", d);
+    MW_REQUIRE(mode == 1 || mode == 2, "layernorm_act: mode must be 1 or 2");
+    if (rows <= 0) return MW_OK;
+    const int grid = ceil_div(rows, 8);
+    if (mode == 1) layernorm_kernel<4, 1><<<grid, 256, 0, st>>>(x, gamma, beta, out, rows, d);
+    else layernorm_kernel<4, 2><<<grid, 256, 0, st>>>(x, gamma, beta, out, rows, d);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

@@ -35,6 +35,20 @@ class W2vDims:
 
 
 
+def effective_pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """The positional conv's weight [d, d/groups, taps] with its weight-norm parametrisation folded in (norm over every
+    dim but the tap axis: modeling_wav2vec2.py:337-355); accepts the plain, ``parametrizations`` and ``weight_g/v`` forms."""
+    p = "wav2vec2.encoder.pos_conv_embed.conv."
+    if p + "weight" in sd:
+        return sd[p + "weight"].float().cpu()
+    if p + "parametrizations.weight.original0" in sd:
+        g, v = sd[p + "parametrizations.weight.original0"], sd[p + "parametrizations.weight.original1"]
+    else:
+        g, v = sd[p + "weight_g"], sd[p + "weight_v"]
+    g, v = g.float().cpu(), v.float().cpu()
+    return v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))
+
+
 def random_init_w2v(dims: W2vDims, seed: int = 0, std: float = 0.05) -> Dict[str, torch.Tensor]:
     """Seeded random-init weights with the Hugging Face ``Wav2Vec2ForCTC`` key names; every matrix is bf16-representable so
     the CUDA engine and this oracle hold identical values.  The positional conv is stored as its effective weight."""

@@ -18,7 +18,7 @@ def _stream():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1, 128, 64), (257, 384, 240), (1500, 1280, 1280), (3000, 1152, 384),
-                                   (4096, 5120, 1280), (777, 256, 5120)])
+                                   (4096, 5120, 1280), (777, 256, 5120), (300, 64, 1024), (100, 32, 128)])
 @pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_resid_f32"])
 def test_gemm(lib, M, N, K, mode):
     from manual_whisper_b200 import _lib

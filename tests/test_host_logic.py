@@ -131,8 +131,7 @@ def test_shim_exposes_the_names_transcribe_py_uses():
         wx = importlib.import_module("whisperx")
         for name in ("load_model", "load_audio", "load_align_model", "align", "DiarizationPipeline", "assign_word_speakers"):
             assert hasattr(wx, name)
-        res = wx.align([{"text": "a", "start": 0.0, "end": 1.0}], None, {}, None, "cuda", return_char_alignments=False)
-        assert res["segments"][0]["text"] == "a"
+        assert wx.align is mw.align and wx.load_align_model is mw.load_align_model
         with pytest.raises(RuntimeError):
             wx.DiarizationPipeline(use_auth_token=None, device="cuda")
     finally:
