@@ -39,6 +39,9 @@ DEFAULT_DICTIONARY = {c: i for i, c in enumerate(
     ["<pad>", "<s>", "</s>", "<unk>", "|", "e", "t", "a", "o", "n", "i", "h", "s", "r", "d", "l", "u", "m", "w", "c", "f", "g",
      "y", "p", "b", "v", "k", "'", "x", "j", "q", "z"])}
 
+# architecture used when no checkpoint is given (None = XLSR-53 large); tests shrink it
+DEFAULT_ALIGN_DIMS: Optional[W2vDims] = None
+
 _LAYER = ["ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2"]
 _N_GLOBAL = 38      # enum mw_w2v_weight_id: MW_A_GLOBAL_COUNT
 
@@ -208,6 +211,8 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
             dims = W2vDims(name=model_name or "checkpoint", n_layers=n_layers, d_model=d, n_heads=d // 64,
                            ffn=sd["wav2vec2.encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0],
                            vocab=sd["lm_head.weight"].shape[0])
+        elif DEFAULT_ALIGN_DIMS is not None:
+            dims = DEFAULT_ALIGN_DIMS
         else:
             dims = W2vDims(vocab=max(dictionary.values()) + 1)
     if sd is None:

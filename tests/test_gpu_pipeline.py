@@ -156,3 +156,30 @@ def test_load_model_from_safetensors_checkpoint(setup, tmp_path):
     want = [s["tokens"] for s in pipe.transcribe(audio, batch_size=4)["segments"]]
     assert [s["tokens"] for s in by_path.transcribe(audio, batch_size=4)["segments"]] == want
     assert [s["tokens"] for s in by_root.transcribe(audio, batch_size=4)["segments"]] == want
+
+
+def test_reference_flow_through_the_whisperx_shim(setup, monkeypatch):
+    """/root/reference/transcribe.py:107-131 verbatim in shape: load_model -> transcribe -> load_align_model -> align, with
+    `import whisperx` resolving to the shim."""
+    import importlib, os, sys
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    from manual_whisper_b200 import alignment
+    from manual_whisper_b200.w2v import W2vDims
+    monkeypatch.setattr(alignment, "DEFAULT_ALIGN_DIMS",
+                        W2vDims(name="w2v-test", n_layers=2, d_model=128, n_heads=2, ffn=256, vocab=32, conv_dim=128, pos_kernel=16, pos_groups=2))
+    shim = os.path.join(os.path.dirname(mw.__file__), "shim")
+    sys.path.insert(0, shim)
+    try:
+        whisperx = importlib.import_module("whisperx")
+        result = pipe.transcribe(audio, batch_size=4, language="en")
+        with pytest.warns(UserWarning, match="random-init"):
+            model_a, metadata = whisperx.load_align_model(language_code="en", device="cuda")
+        aligned = whisperx.align(result["segments"], model_a, metadata, audio, "cuda", return_char_alignments=False)
+    finally:
+        sys.path.remove(shim)
+        sys.modules.pop("whisperx", None)
+    assert set(aligned) == {"segments", "word_segments"} and len(aligned["segments"]) >= len(result["segments"])
+    for seg in aligned["segments"]:
+        assert {"start", "end", "text", "words"} <= set(seg)
+        assert all("word" in w for w in seg["words"])
+    assert sum(len(s["words"]) for s in aligned["segments"]) == len(aligned["word_segments"]) > 0
