@@ -250,6 +250,17 @@ mw_status mw_ctc_align(const float* d_emissions, int64_t window_stride, int voca
                        int32_t* d_frame_token, float* d_frame_score, int max_frames, int32_t* d_ok,
                        float* d_workspace, void* stream);
 
+/* ------------------------------------------------------------------ audio decode -----------
+ * The PCM leg of whisperx.load_audio (/root/reference/transcribe.py:117; `ffmpeg -ac 1 -ar 16000 -f s16le` then /32768):
+ * interleaved PCM (sample_format 0 = int16, 1 = float32) [n_frames, channels] at rate orig*g -> mono float32 at new_rate*g
+ * (orig:new_rate the reduced ratio).  d_kernels: f32 [new_rate, taps] polyphase windowed-sinc taps, taps = 2*width + orig
+ * (torchaudio.functional.resample's filter, built by manual_whisper_b200/audio.py); d_lo_hi: int32 [new_rate, 2] non-zero
+ * tap range of each phase.  d_out: f32 [n_out], n_out <= ceil(n_frames * new_rate / orig).  quantize_s16 != 0 rounds to
+ * the int16 grid like the s16le pipe. */
+mw_status mw_pcm_resample(const void* d_pcm, int64_t n_frames, int channels, int sample_format, int orig, int new_rate,
+                          const float* d_kernels, const int32_t* d_lo_hi, int taps, int width, float* d_out,
+                          int64_t n_out, int quantize_s16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ hand-written CUDA behind the C ABI of include/mw_b200.h (libmw_b200.so); importi
 imports the CPU oracle, and every call fails loudly if the CUDA library is missing.
 """
 from .config import SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES, model_dims, special_tokens
-from .audio import load_audio, log_mel_spectrogram, pad_or_trim, mel_filters
+from .audio import load_audio, load_audio_device, decode_pcm_device, log_mel_spectrogram, pad_or_trim, mel_filters
 from .asr import load_model, FasterWhisperPipeline, WhisperModel, TranscriptionOptions, get_prompt
 from .vad import merge_chunks, InjectedVad, EnergyVad, GpuEnergyVad, synthetic_speech
 from .tokenizer import Tokenizer
@@ -16,6 +16,7 @@ from .w2v import W2vDims, random_init_w2v
 
 __version__ = "0.1.0"
 __all__ = [
+    "load_audio_device", "decode_pcm_device",
     "load_align_model", "align", "AlignModel", "AlignEngine", "W2vDims", "random_init_w2v",
     "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
     "load_audio", "log_mel_spectrogram", "pad_or_trim", "mel_filters", "load_model", "FasterWhisperPipeline",

@@ -77,6 +77,8 @@ SIGNATURES = {
     "mw_w2v_frames": (C.c_int32, [C.c_int64]),
     "mw_w2v_emissions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_i32p, C.c_int, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
+    "mw_pcm_resample": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "mw_ctc_align": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

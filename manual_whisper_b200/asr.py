@@ -194,13 +194,23 @@ class FasterWhisperPipeline:
                    _forced_eot_len: int = 0) -> Dict:
         if isinstance(audio, str):
             audio = load_audio(audio)
+        resident = None
+        if torch.is_tensor(audio) and audio.is_cuda:
+            # already decoded on the GPU (audio.load_audio_device / decode_pcm_device): no H2D copy at all
+            d_audio = audio.to(torch.float32).reshape(-1).contiguous()
+            resident = {"lo": 0, "audio": {dev: d_audio.to(dev) for dev in {rep.device for rep in self.replicas}}}
+            audio = d_audio.cpu().numpy()
+        elif torch.is_tensor(audio):
+            audio = audio.numpy()
         audio = np.ascontiguousarray(audio, dtype=np.float32)
         if audio.ndim != 1:
             raise ValueError("audio must be a mono 1-D float array at 16 kHz")
 
         # ---- VAD -> windows
-        resident = None
-        if getattr(self.vad_model, "wants_device", False):
+        if resident is not None:
+            waveform = resident["audio"][self.device].unsqueeze(0) if getattr(self.vad_model, "wants_device", False) \
+                else torch.from_numpy(audio).unsqueeze(0)
+        elif getattr(self.vad_model, "wants_device", False):
             # device-side VAD: one H2D copy of the whole waveform serves the VAD and every ASR batch
             resident = self.upload(audio, np.array([0], dtype=np.int64), np.array([len(audio)], dtype=np.int64))
             waveform = resident["audio"][self.device].unsqueeze(0)

@@ -27,8 +27,9 @@ TOKENS_PER_SECOND = SAMPLE_RATE // N_SAMPLES_PER_TOKEN
 
 def load_audio(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
     """File -> mono float32 at 16 kHz in [-1, 1) (``ffmpeg ... -f s16le -ac 1 -ar 16000``,
-    then int16/32768).  ffmpeg is used when present; 16-bit PCM WAV files at `sr` (the format the
-    reference's web recorder produces, /root/reference/web/audioRecorder.js:100-127) are read directly."""
+    then int16/32768).  ffmpeg is used when present; otherwise 16-bit PCM WAV files (the format the reference's web
+    recorder produces, /root/reference/web/audioRecorder.js:100-127) are read directly, and any other rate or channel
+    count goes through the GPU decoder (mw_pcm_resample: channel mean + band-limited resampling + s16 quantisation)."""
     ffmpeg = shutil.which("ffmpeg")
     if ffmpeg:
         cmd = [ffmpeg, "-nostdin", "-threads", "0", "-i", file, "-f", "s16le", "-ac", "1",
@@ -38,18 +39,89 @@ def load_audio(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
         except subprocess.CalledProcessError as e:
             raise RuntimeError(f"Failed to load audio: {e.stderr.decode()}") from e
         return np.frombuffer(out, np.int16).flatten().astype(np.float32) / 32768.0
+    pcm, channels, rate = _read_wav_pcm16(file)
+    if rate == sr:
+        if channels > 1:
+            pcm = pcm.reshape(-1, channels).astype(np.int32).sum(axis=1) // channels
+        return pcm.astype(np.float32) / 32768.0
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            f"Failed to load audio: without ffmpeg, {channels}-channel {rate} Hz WAV needs the GPU decoder "
+            f"(mw_pcm_resample) and no CUDA device is available; only mono 16-bit PCM WAV at {sr} Hz is readable on the host")
+    return decode_pcm_device(pcm, channels, rate, sr).cpu().numpy()
+
+
+def _read_wav_pcm16(file: str):
     try:
         with wave.open(file, "rb") as w:
-            if w.getsampwidth() != 2 or w.getframerate() != sr:
-                raise RuntimeError(
-                    f"Failed to load audio: without ffmpeg only 16-bit PCM WAV at {sr} Hz is readable "
-                    f"(got {8 * w.getsampwidth()}-bit at {w.getframerate()} Hz)")
-            pcm = np.frombuffer(w.readframes(w.getnframes()), np.int16)
-            if w.getnchannels() > 1:
-                pcm = pcm.reshape(-1, w.getnchannels()).astype(np.int32).sum(axis=1) // w.getnchannels()
-            return pcm.astype(np.float32) / 32768.0
+            if w.getsampwidth() != 2:
+                raise RuntimeError(f"Failed to load audio: without ffmpeg only 16-bit PCM WAV is readable (got {8 * w.getsampwidth()}-bit)")
+            pcm = np.frombuffer(bytearray(w.readframes(w.getnframes())), np.int16)      # writable: torch.from_numpy needs it
+            return pcm, w.getnchannels(), w.getframerate()
     except (wave.Error, EOFError, OSError) as e:
         raise RuntimeError(f"Failed to load audio: {e} (ffmpeg is not installed)") from e
+
+
+@lru_cache(maxsize=16)
+def sinc_resample_kernel(orig: int, new: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Polyphase windowed-sinc taps of ``torchaudio.functional.resample`` (sinc_interp_hann) for the rate pair, as numpy:
+    (kernels f32 [new', 2*width + orig'], lo_hi i32 [new', 2] non-zero tap range per phase, width, orig', new') with
+    orig':new' the reduced ratio.  Evaluated in float64 and cast, as upstream does (its phase offsets are fp32)."""
+    import math
+    g = math.gcd(int(orig), int(new))
+    orig, new = int(orig) // g, int(new) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    phase = (np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)[:, None]
+    t = np.clip((phase + idx) * base, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = (np.where(t == 0, 1.0, np.sin(t) / t) * window * (base / orig)).astype(np.float32)
+    lo_hi = np.zeros((new, 2), dtype=np.int32)
+    for i in range(new):
+        nz = np.nonzero(k[i])[0]
+        lo_hi[i] = (nz[0], nz[-1] + 1) if len(nz) else (0, 0)
+    return k, lo_hi, width, orig, new
+
+
+def decode_pcm_device(pcm, channels: int, rate: int, sr: int = SAMPLE_RATE, device=None, quantize_s16: bool = True) -> torch.Tensor:
+    """Interleaved PCM (int16 or float32; numpy or a CUDA tensor) at `rate` Hz -> mono float32 at `sr` Hz ON THE DEVICE:
+    channel mean, band-limited resampling and the s16le pipe's quantisation in one kernel (include/mw_b200.h:
+    mw_pcm_resample).  The result can be passed straight to ``model.transcribe``."""
+    import math
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("decode_pcm_device needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    device = torch.device(device if device is not None else "cuda")
+    x = pcm if torch.is_tensor(pcm) else torch.from_numpy(np.ascontiguousarray(pcm))
+    if x.dtype not in (torch.int16, torch.float32):
+        raise ValueError(f"PCM must be int16 or float32, got {x.dtype}")
+    x = x.reshape(-1).to(device).contiguous()
+    if channels < 1 or x.numel() % channels:
+        raise ValueError(f"{x.numel()} samples do not divide into {channels} channels")
+    n_frames = x.numel() // channels
+    k, lo_hi, width, o, n = sinc_resample_kernel(int(rate), int(sr))
+    if o == n:      # same rate: no filtering (as torchaudio / ffmpeg), the kernel only mixes channels and quantises
+        k, lo_hi, width = np.ones((1, 1), np.float32), np.array([[0, 1]], np.int32), 0
+    n_out = int(math.ceil(n * n_frames / o))
+    out = torch.empty(n_out, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        d_k = torch.from_numpy(k).to(device)
+        d_lh = torch.from_numpy(lo_hi).to(device)
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.mw_pcm_resample(x.data_ptr(), n_frames, int(channels), 0 if x.dtype == torch.int16 else 1, o, n,
+                                       d_k.data_ptr(), d_lh.data_ptr(), k.shape[1], width, out.data_ptr(), n_out,
+                                       int(bool(quantize_s16)), st), "mw_pcm_resample")
+    return out
+
+
+def load_audio_device(file: str, sr: int = SAMPLE_RATE, device=None) -> torch.Tensor:
+    """16-bit PCM WAV (any rate, any channel count) -> mono float32 at `sr` Hz resident on the GPU, without ffmpeg and
+    without a host round trip of the decoded waveform."""
+    pcm, channels, rate = _read_wav_pcm16(file)
+    return decode_pcm_device(pcm, channels, rate, sr, device)
 
 
 def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):

@@ -145,3 +145,22 @@ def test_load_model_rejects_non_whisper_checkpoint(tmp_path):
     save_file({"foo": torch.zeros(2)}, bad)
     with pytest.raises(ValueError, match="not a Hugging Face Whisper checkpoint"):
         mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", model=bad)
+
+
+def test_sinc_resample_kernel_matches_oracle_and_wav_rate_error(tmp_path):
+    import wave
+    from manual_whisper_b200.audio import sinc_resample_kernel
+    from oracle.resample import sinc_kernel
+    for orig in (48000, 44100, 8000):
+        k, lo_hi, width, o, n = sinc_resample_kernel(orig, 16000)
+        k2, w2, o2, n2 = sinc_kernel(orig, 16000)
+        assert (width, o, n) == (w2, o2, n2) and np.array_equal(k, k2)
+        for i in range(n):
+            assert np.all(k[i, : lo_hi[i, 0]] == 0) and np.all(k[i, lo_hi[i, 1]:] == 0)
+    p = str(tmp_path / "hi.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000)
+        w.writeframes(np.zeros(9600, np.int16).tobytes())
+    if not torch.cuda.is_available() and not __import__("shutil").which("ffmpeg"):
+        with pytest.raises(RuntimeError, match="GPU decoder"):
+            mw.load_audio(p)
