@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-repeats", type=int, default=1)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: do not time the public-API pass")
+    ap.add_argument("--merge", type=int, default=1, help="user batches of 32 windows merged into one device batch (rows are independent)")
     ap.add_argument("--streams", type=int, default=8, help="batches in flight per GPU (shared-weight replicas)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -226,7 +227,7 @@ def main():
     pinned.numpy()[:] = audio_np
     audio_host = pinned.numpy()
     pipe = mw.load_model(MODEL, "cuda", device_index=local, compute_type="bfloat16", language="zh",
-                         asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), model=sd, max_batch=BATCH,
+                         asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), model=sd, max_batch=BATCH * args.merge,
                          streams_per_device=args.streams)
     del sd
     model = pipe.model
@@ -240,7 +241,7 @@ def main():
     def run_steps(first, count):
         """`count` steps = batches (first+i) % n_full of the recording, dispatched to the in-flight replicas."""
         idx = np.concatenate([np.arange(((first + i) % n_full) * BATCH, ((first + i) % n_full + 1) * BATCH) for i in range(count)])
-        pipe.run_device_batches(resident, offs[idx], lens32[idx], BATCH)
+        pipe.run_device_batches(resident, offs[idx], lens32[idx], BATCH * args.merge)
         return float(lens[idx].sum()) / 16000.0
 
     def barrier():
@@ -253,7 +254,7 @@ def main():
     # then the W warm-up steps through the normal dynamic queue
     for rep in pipe.replicas:
         with torch.cuda.device(rep.device):
-            sl = slice(0, BATCH)
+            sl = slice(0, BATCH * args.merge)
             rep.transcribe_windows(resident["audio"][rep.device], torch.from_numpy(offs[sl] - resident["lo"]).to(rep.device),
                                    torch.from_numpy(lens32[sl]).to(rep.device), pipe.tokenizer, pipe.options)
     torch.cuda.synchronize()
@@ -278,7 +279,7 @@ def main():
     for _ in range(0 if args.skip_e2e else max(1, args.e2e_repeats)):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        result = pipe.transcribe(audio_host, batch_size=BATCH, language="zh")
+        result = pipe.transcribe(audio_host, batch_size=BATCH * args.merge, language="zh")
         torch.cuda.synchronize()
         t_e2e.append(time.perf_counter() - t0)
     e2e_s = min(t_e2e) if t_e2e else float('inf')

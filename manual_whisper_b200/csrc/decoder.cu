@@ -175,53 +175,64 @@ skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bflo
 // Main version: a CTA owns 16 weight rows and the whole K; its NW warps split K into contiguous runs of KB
 // 32-element blocks and issue EVERY weight load (ld.global.nc, L1 no-allocate) before touching
 // anything else, so a kernel's whole matrix is in flight at once.
-template <int KB, int NW>
-__global__ void __launch_bounds__(NW * 32)
+template <int KB, int NW, int WT>
+__global__ void __launch_bounds__(NW * 32, WT == 2 ? 2 : 1)
 skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
                           const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                           int flags) {
-    __shared__ float red[NW][32][17];
+    // WT = 16-row weight tiles per CTA.  Every CTA re-reads the whole X block [32, K] from L2, so with one tile the L2->SM
+    // traffic is 3x the HBM traffic and caps several batches in flight at ~3.3 TB/s of weights; two tiles halve the X share.
+    __shared__ float red[NW][32][WT * 16 + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int n0 = blockIdx.x * 16, r0 = blockIdx.y * 32;
+    const int n0 = blockIdx.x * (16 * WT), r0 = blockIdx.y * 32;
     const int k_start = warp * (KB * 32) + q * 8;
-    const __nv_bfloat16* wa = W + (int64_t)min(n0 + g, N - 1) * ldw + k_start;
-    const __nv_bfloat16* wb = W + (int64_t)min(n0 + g + 8, N - 1) * ldw + k_start;
-    uint4 alo[KB], ahi[KB];
+    uint4 alo[WT][KB], ahi[WT][KB];
 #pragma unroll
-    for (int i = 0; i < KB; ++i) {
-        alo[i] = ldg_stream(wa + i * 32);
-        ahi[i] = ldg_stream(wb + i * 32);
+    for (int wt = 0; wt < WT; ++wt) {
+        const __nv_bfloat16* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
+        const __nv_bfloat16* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            alo[wt][i] = ldg_stream(wa + i * 32);
+            ahi[wt][i] = ldg_stream(wb + i * 32);
+        }
     }
     const __nv_bfloat16* xr[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xr[t] = X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + k_start;
-    float c[4][4];
+    float c[WT][4][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int wt = 0; wt < WT; ++wt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c[t][i] = 0.0f;
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[wt][t][i] = 0.0f;
 #pragma unroll
     for (int i = 0; i < KB; ++i) {
         uint4 b[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(xr[t] + i * 32));
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            mma_bf16_16816(c[t], alo[i].x, ahi[i].x, alo[i].y, ahi[i].y, b[t].x, b[t].y);
-            mma_bf16_16816(c[t], alo[i].z, ahi[i].z, alo[i].w, ahi[i].w, b[t].z, b[t].w);
-        }
+        for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                mma_bf16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
+                mma_bf16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
+            }
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        red[warp][t * 8 + 2 * q][g] = c[t][0];
-        red[warp][t * 8 + 2 * q + 1][g] = c[t][1];
-        red[warp][t * 8 + 2 * q][g + 8] = c[t][2];
-        red[warp][t * 8 + 2 * q + 1][g + 8] = c[t][3];
-    }
+    for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            red[warp][t * 8 + 2 * q][wt * 16 + g] = c[wt][t][0];
+            red[warp][t * 8 + 2 * q + 1][wt * 16 + g] = c[wt][t][1];
+            red[warp][t * 8 + 2 * q][wt * 16 + g + 8] = c[wt][t][2];
+            red[warp][t * 8 + 2 * q + 1][wt * 16 + g + 8] = c[wt][t][3];
+        }
     __syncthreads();
-    for (int o = threadIdx.x; o < 512; o += NW * 32) {
-        const int rl = o >> 4, nl = o & 15;
+    for (int o = threadIdx.x; o < 32 * 16 * WT; o += NW * 32) {
+        const int rl = o / (16 * WT), nl = o % (16 * WT);
         const int r = r0 + rl, n = n0 + nl;
         float v = 0.0f;
 #pragma unroll
@@ -240,9 +251,10 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
 template <int KB, int NW>
 mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
                         int ldo, int R, int N, int K, int flags, cudaStream_t st) {
-    dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
-    skinny_gemm_rows16_kernel<KB, NW><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias,
-                                                                resid, out, ldo, R, N, K, flags);
+    constexpr int WT = (NW <= 8 && KB <= 5) ? 2 : 1;          // two weight tiles where the registers allow it
+    dim3 grid(ceil_div(N, 16 * WT), ceil_div(R, 32));
+    skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias,
+                                                                    resid, out, ldo, R, N, K, flags);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -747,12 +759,24 @@ __device__ void row_rules_and_stats(float* lg, int V, const RowRule& rr, const G
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tb = o.timestamp_begin;
     ValIdx m_txt{-INFINITY, 0x7fffffff}, m_ts{-INFINITY, 0x7fffffff};
-    for (int i = tid; i < V; i += SEL_THREADS) {
-        float v = lg[i];
-        if (is_masked(i, rr, o, sup, beg)) { v = -INFINITY; lg[i] = v; }
-        ValIdx c{v, i};
-        if (o.with_timestamps && i >= tb) m_ts = better(m_ts, c);
-        else m_txt = better(m_txt, c);
+    // four independent loads per thread per trip: the row is 207 KB and a one-load-at-a-time loop is pure latency
+    constexpr int UNR = 4;
+    for (int i0 = tid; i0 < V; i0 += UNR * SEL_THREADS) {
+        float v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SEL_THREADS;
+            v[u] = i < V ? lg[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SEL_THREADS;
+            if (i >= V) break;
+            if (is_masked(i, rr, o, sup, beg)) { v[u] = -INFINITY; lg[i] = v[u]; }
+            ValIdx c{v[u], i};
+            if (o.with_timestamps && i >= tb) m_ts = better(m_ts, c);
+            else m_txt = better(m_txt, c);
+        }
     }
     m_txt = warp_best(m_txt);
     m_ts = warp_best(m_ts);
@@ -766,10 +790,20 @@ __device__ void row_rules_and_stats(float* lg, int V, const RowRule& rr, const G
     __syncthreads();
     const float gm = b_all.v;
     float sum_all = 0.0f, sum_ts = 0.0f;
-    for (int i = tid; i < V; i += SEL_THREADS) {
-        const float e = __expf(lg[i] - gm);      // exp(-inf) = 0
-        sum_all += e;
-        if (o.with_timestamps && i >= tb) sum_ts += e;
+    for (int i0 = tid; i0 < V; i0 += UNR * SEL_THREADS) {
+        float v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SEL_THREADS;
+            v[u] = i < V ? lg[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SEL_THREADS;
+            const float e = __expf(v[u] - gm);      // exp(-inf) = 0
+            sum_all += e;
+            if (o.with_timestamps && i >= tb) sum_ts += e;
+        }
     }
     sum_all = warp_sum(sum_all);
     sum_ts = warp_sum(sum_ts);
