@@ -902,15 +902,25 @@ beam_candidates_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts
     ValIdx loc[NCAND];
 #pragma unroll
     for (int j = 0; j < NCAND; ++j) loc[j] = ValIdx{-INFINITY, 0x7fffffff};
-    for (int i = tid; i < V; i += SEL_THREADS) {
-        ValIdx c{lg[i], i};
-        if (c.v == -INFINITY) continue;
-        if (c.v > loc[NCAND - 1].v || (c.v == loc[NCAND - 1].v && c.i < loc[NCAND - 1].i)) {
-            loc[NCAND - 1] = c;
+    constexpr int UNR = 4;      // independent loads per trip (same element order per thread as a plain strided loop)
+    for (int i0 = tid; i0 < V; i0 += UNR * SEL_THREADS) {
+        float v[UNR];
 #pragma unroll
-            for (int j = NCAND - 1; j > 0; --j) {
-                const bool up = loc[j].v > loc[j - 1].v || (loc[j].v == loc[j - 1].v && loc[j].i < loc[j - 1].i);
-                if (up) { ValIdx t = loc[j - 1]; loc[j - 1] = loc[j]; loc[j] = t; }
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * SEL_THREADS;
+            v[u] = i < V ? lg[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            ValIdx c{v[u], i0 + u * SEL_THREADS};
+            if (c.v == -INFINITY) continue;
+            if (c.v > loc[NCAND - 1].v || (c.v == loc[NCAND - 1].v && c.i < loc[NCAND - 1].i)) {
+                loc[NCAND - 1] = c;
+#pragma unroll
+                for (int j = NCAND - 1; j > 0; --j) {
+                    const bool up = loc[j].v > loc[j - 1].v || (loc[j].v == loc[j - 1].v && loc[j].i < loc[j - 1].i);
+                    if (up) { ValIdx t = loc[j - 1]; loc[j - 1] = loc[j]; loc[j] = t; }
+                }
             }
         }
     }
@@ -1699,7 +1709,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
 }
 
 // ---- measurement hook: average ms of one decode step restricted to the kernel classes in `parts`
-// (1 embed, 2 LayerNorm, 4 skinny GEMMs, 8 self-attention, 16 cross-attention, 32 logits GEMM, 64 select), replayed as a CUDA graph.
+// (1 embed, 2 LayerNorm, 4 skinny GEMMs, 8 self-attention, 16 cross-attention, 32 logits GEMM), replayed as a CUDA graph.
 extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, float* h_ms_avg, void* stream) {
     MW_REQUIRE(m && h_ms_avg && iters > 0, "mw_bench_step: bad argument");
     const mw_model_config& c = m->cfg;
