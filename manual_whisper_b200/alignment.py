@@ -372,7 +372,8 @@ def assemble_segment(segment: dict, text: str, clean_cdx: List[int], char_spans,
 
 def align(transcript: Iterable[dict], model: AlignModel, align_model_metadata: dict, audio, device: str = "cuda",
           interpolate_method: str = "nearest", return_char_alignments: bool = False, print_progress: bool = False,
-          combined_progress: bool = False, *, sentence_splitter: Optional[Callable[[str], List[Tuple[int, int]]]] = None) -> dict:
+          combined_progress: bool = False, *, sentence_splitter: Optional[Callable[[str], List[Tuple[int, int]]]] = None,
+          _keep_index: bool = False) -> dict:
     """whisperx.align(transcript, model, align_model_metadata, audio, device, ...) ->
     {"segments": [{"start","end","text","words":[{"word","start","end","score"}], ("chars")}], "word_segments": [...]}."""
     if isinstance(audio, str):
@@ -443,6 +444,10 @@ def align(transcript: Iterable[dict], model: AlignModel, align_model_metadata: d
         if print_progress:
             pct = done / max(len(todo), 1) * 100
             print(f"Progress: {50 + pct / 2 if combined_progress else pct:.2f}%...")
+    if _keep_index:         # distributed.align_sharded: tag every output sub-segment with the input segment it came from
+        for seg, group in zip(transcript, out_segments):
+            for s in group or []:
+                s["_idx"] = seg.get("_idx")
     segments = [s for group in out_segments for s in (group or [])]
     word_segments = [w for s in segments for w in s["words"]]
     return {"segments": segments, "word_segments": word_segments}

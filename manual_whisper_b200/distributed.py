@@ -56,3 +56,26 @@ def transcribe_sharded(pipeline, audio, batch_size: int, rank: int, world: int, 
             local.append((a + k, seg))
     segs = gather_ordered(local, len(windows), group)
     return {"segments": segs, "language": kwargs.get("language") or pipeline.preset_language}
+
+
+def align_sharded(transcript, model_a, metadata, audio, rank: int, world: int, group=None, *, batch_size: int = 16,
+                  align_fn=None, **kwargs):
+    """whisperx.align across `world` single-GPU processes (the step after the path): segments are
+    independent units, so batches of `batch_size` segments are dealt round-robin, every rank aligns its share on its own
+    GPU, and the per-segment results are gathered in segment order.  Same return value on every rank."""
+    from .alignment import align
+    align_fn = align_fn or align
+    transcript = list(transcript)
+    local = []
+    for a, b in shard_batches(len(transcript), batch_size, world, rank):
+        # one call per batch keeps the GPU batching; a segment may come back as several sentence sub-segments, so each
+        # input carries its index through the call and the outputs are regrouped by it
+        tagged = [dict(seg, _idx=i) for i, seg in zip(range(a, b), transcript[a:b])]
+        per_seg = {i: [] for i in range(a, b)}
+        out = align_fn(tagged, model_a, metadata, audio, _keep_index=True, **kwargs)["segments"]
+        for s_ in out:
+            per_seg[s_.pop("_idx")].append(s_)
+        local += [(i, per_seg[i]) for i in range(a, b)]
+    groups = gather_ordered(local, len(transcript), group) if transcript else []
+    segments = [s for g in groups for s in g]
+    return {"segments": segments, "word_segments": [w for s in segments for w in s["words"]]}

@@ -57,3 +57,43 @@ def test_gather_detects_missing_and_duplicate_windows():
         gather_ordered([(0, "a")], 2)
     with pytest.raises(RuntimeError, match="two ranks"):
         gather_ordered([(0, "a"), (0, "b")], 1)
+
+
+def _fake_align(transcript, model, metadata, audio, _keep_index=False, **kw):
+    """Stands in for the GPU alignment: splits every segment into one sub-segment per sentence-ish chunk."""
+    segs = []
+    for seg in transcript:
+        parts = seg["text"].split(".")
+        for k, p in enumerate(x for x in parts if x):
+            s = {"text": p, "start": seg["start"] + k, "end": seg["start"] + k + 1, "words": [{"word": w} for w in p.split()]}
+            if _keep_index:
+                s["_idx"] = seg.get("_idx")
+            segs.append(s)
+    return {"segments": segs, "word_segments": [w for s in segs for w in s["words"]]}
+
+
+def _align_worker(rank, world, port, q):
+    from manual_whisper_b200.distributed import align_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        transcript = [{"text": f"a{i} b{i}.c{i}" if i % 3 == 0 else f"x{i}", "start": 10.0 * i, "end": 10.0 * i + 5} for i in range(11)]
+        got = align_sharded(transcript, None, {}, None, rank, world, batch_size=2, align_fn=_fake_align)
+        want = _fake_align(transcript, None, {}, None)
+        q.put((rank, got == want, len(got["segments"])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_align_sharded_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_align_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res) and all(n == 15 for _, _, n in res)
