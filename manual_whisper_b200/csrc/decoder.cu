@@ -248,13 +248,113 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
     }
 }
 
+// K = 5120-class shapes (16 warps): the same two-tile idea needs 160 weight registers, so K is walked in two halves of
+// KB blocks per warp (weights of one half in flight at a time) and the 16 warps reduce through 8 shared-memory slots.
+template <int KB, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+skinny_gemm_rows32_khalf_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+                                const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
+                                int flags) {
+    static_assert(NW == 16, "two rounds through 8 reduction slots");
+    constexpr int WT = 2;
+    __shared__ float red[NW / 2][32][WT * 16 + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int n0 = blockIdx.x * (16 * WT), r0 = blockIdx.y * 32;
+    float c[WT][4][4];
+#pragma unroll
+    for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[wt][t][i] = 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k_start = h * (NW * KB * 32) + warp * (KB * 32) + q * 8;
+        uint4 alo[WT][KB], ahi[WT][KB];
+#pragma unroll
+        for (int wt = 0; wt < WT; ++wt) {
+            const __nv_bfloat16* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
+            const __nv_bfloat16* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
+#pragma unroll
+            for (int i = 0; i < KB; ++i) {
+                alo[wt][i] = ldg_stream(wa + i * 32);
+                ahi[wt][i] = ldg_stream(wb + i * 32);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            uint4 b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                b[t] = __ldg(reinterpret_cast<const uint4*>(X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + k_start + i * 32));
+#pragma unroll
+            for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    mma_bf16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
+                    mma_bf16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
+                }
+        }
+    }
+    // warps 8..15 park their partial sums, warps 0..7 fold them in (same fragment positions), then the usual 8-slot reduce
+    const int slot = warp & 7;
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        if ((warp >= 8) == (round == 0)) {
+#pragma unroll
+            for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float* r0p = &red[slot][t * 8 + 2 * q][wt * 16 + g];
+                    float* r1p = &red[slot][t * 8 + 2 * q + 1][wt * 16 + g];
+                    if (round == 1) { c[wt][t][0] += r0p[0]; c[wt][t][1] += r1p[0]; c[wt][t][2] += r0p[8]; c[wt][t][3] += r1p[8]; }
+                    r0p[0] = c[wt][t][0]; r1p[0] = c[wt][t][1]; r0p[8] = c[wt][t][2]; r1p[8] = c[wt][t][3];
+                }
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < 32 * 16 * WT; o += NW * 32) {
+        const int rl = o / (16 * WT), nl = o % (16 * WT);
+        const int r = r0 + rl, n = n0 + nl;
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW / 2; ++w) v += red[w][rl][nl];
+        if (r < R && n < N) {
+            if (bias) v += __ldg(bias + n);
+            if (flags & SK_FLAG_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+            const int64_t oi = (int64_t)r * ldo + n;
+            if (resid) v += resid[oi];
+            if (flags & SK_FLAG_F32) reinterpret_cast<float*>(out)[oi] = v;
+            else reinterpret_cast<__nv_bfloat16*>(out)[oi] = __float2bfloat16(v);
+        }
+    }
+}
+
 template <int KB, int NW>
 mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
                         int ldo, int R, int N, int K, int flags, cudaStream_t st) {
     constexpr int WT = (NW <= 8 && KB <= 5) ? 2 : 1;          // two weight tiles where the registers allow it
-    dim3 grid(ceil_div(N, 16 * WT), ceil_div(R, 32));
-    skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias,
-                                                                    resid, out, ldo, R, N, K, flags);
+    static const bool one_tile = [] { const char* e = getenv("MW_SKINNY_WT"); return e && e[0] == '1'; }();   // A/B hook
+    if constexpr (NW == 16 && KB % 2 == 0 && KB / 2 <= 5) {
+        static const bool no_khalf = [] { const char* e = getenv("MW_SKINNY_KHALF"); return e && e[0] == '0'; }();
+        if (!one_tile && !no_khalf) {
+            dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
+            skinny_gemm_rows32_khalf_kernel<KB / 2, NW><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W,
+                                                                                  ldw, bias, resid, out, ldo, R, N, K, flags);
+            MW_LAUNCH_CHECK();
+            return MW_OK;
+        }
+    }
+    if (WT == 2 && !one_tile) {
+        dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
+        skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw,
+                                                                        bias, resid, out, ldo, R, N, K, flags);
+    } else {
+        dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
+        skinny_gemm_rows16_kernel<KB, NW, 1><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw,
+                                                                       bias, resid, out, ldo, R, N, K, flags);
+    }
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
