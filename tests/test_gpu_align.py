@@ -142,3 +142,16 @@ def test_full_size_model_matches_oracle(vocab):
         spread = (ref.max() - ref.min()).item()
         err = (em[c, :T] - ref).abs().max().item()
         assert err <= 0.03 * spread, (c, err, spread)
+
+
+def test_ctc_kernel_against_golden_vector(small):
+    import os
+    _, eng = small
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows_golden.npz"))
+    em = g["ctc_emission"]
+    pad = np.full((em.shape[0], SMALL.vocab), -30.0, dtype=np.float32)      # the engine's vocabulary is wider: unused symbols
+    pad[:, : em.shape[1]] = em
+    ft, fs, ok = eng.ctc_align(torch.from_numpy(pad[None]).cuda(), np.array([em.shape[0]], dtype=np.int32),
+                               [[int(t) for t in g["ctc_tokens"]]], blank=0)
+    assert ok[0] and np.array_equal(ft[0], g["ctc_frame_tokens"])
+    assert np.allclose(fs[0], g["ctc_frame_scores"], rtol=1e-5, atol=1e-7)

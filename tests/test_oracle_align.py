@@ -111,3 +111,26 @@ def test_backtrack_reports_unalignable():
     em = np.log(np.full((3, 4), 0.25, dtype=np.float32))
     tokens = [1, 2, 3, 1, 2]
     assert OA.backtrack(OA.get_trellis(em, tokens), em, tokens) is None
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows_golden.npz"))
+
+
+def test_oracles_against_committed_golden_vectors():
+    """Fixtures written by scripts/make_golden_next_rows.py from transformers / torchaudio (and the oracle DP itself)."""
+    from oracle.resample import resample
+    g = _golden()
+    sd = random_init_w2v(SMALL, seed=3)
+    with torch.no_grad():
+        got = OracleWav2Vec2(SMALL, sd).logits(torch.from_numpy(g["w2v_wave"]))
+    assert np.abs(got.numpy() - g["w2v_logits"]).max() < 2e-4 * max(1.0, np.abs(g["w2v_logits"]).max())
+    for rate in (44100, 48000):
+        assert np.abs(resample(g[f"resample_in_{rate}"], rate, 16000) - g[f"resample_out_{rate}"]).max() < 2e-5
+    em, toks = g["ctc_emission"], [int(t) for t in g["ctc_tokens"]]
+    tr = OA.get_trellis(em, toks, 0)
+    path = OA.backtrack(tr, em, toks, 0)
+    assert abs(float(tr[-1, -1]) - float(g["ctc_final_score"])) < 1e-5
+    assert np.array_equal(OA.frame_tokens(path, em.shape[0]), g["ctc_frame_tokens"])
+    assert np.allclose([p.score for p in path], g["ctc_frame_scores"], rtol=1e-6)
