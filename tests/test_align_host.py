@@ -85,3 +85,75 @@ def test_load_align_model_needs_cuda():
         with pytest.warns(UserWarning, match="random-init"), pytest.raises(RuntimeError, match="no CPU fallback"):
             AL.load_align_model("zh", "cuda", dims=W2vDims(name="t", n_layers=1, d_model=128, n_heads=2, ffn=256, vocab=32,
                                                            conv_dim=128, pos_kernel=4, pos_groups=2))
+
+
+class _OracleEngine:
+    """Stands in for AlignEngine on the CPU: oracle emissions + oracle DP behind the same three calls align() makes."""
+
+    def __init__(self, dims, sd, max_batch=2, max_samples=16000 * 8):
+        from oracle.wav2vec2 import OracleWav2Vec2
+        self.model = OracleWav2Vec2(dims, sd)
+        self.dims, self.device, self.max_batch, self.max_samples = dims, torch.device("cpu"), max_batch, max_samples
+        self.calls = []
+
+    def emissions(self, d_audio, offs, lens):
+        frames = np.array([self.dims.frames(max(int(n), 400)) for n in lens], dtype=np.int32)
+        out = torch.zeros(len(offs), int(frames.max()), self.dims.vocab)
+        self.calls.append(len(offs))
+        for c, (o, n) in enumerate(zip(offs, lens)):
+            w = d_audio[int(o): int(o) + int(n)]
+            if len(w) < 400:
+                w = torch.nn.functional.pad(w, (0, 400 - len(w)))
+            with torch.no_grad():
+                out[c, : frames[c]] = self.model.emissions(w)
+        return out, frames
+
+    def ctc_align(self, em, frames, tokens, blank):
+        from oracle import align as OA
+        n, T, _ = em.shape
+        ft, fs, ok = np.zeros((n, T), np.int32), np.zeros((n, T), np.float32), np.zeros(n, bool)
+        for c in range(n):
+            e = em[c, : frames[c]].numpy()
+            if not (0 < len(tokens[c]) <= frames[c]):
+                continue
+            path = OA.backtrack(OA.get_trellis(e, tokens[c], blank), e, tokens[c], blank)
+            if path is None:
+                continue
+            ok[c] = True
+            ft[c, : frames[c]] = OA.frame_tokens(path, int(frames[c]))
+            fs[c, : frames[c]] = [p.score for p in path]
+        return ft, fs, ok
+
+
+def test_align_control_flow_on_cpu_with_an_oracle_engine(capsys):
+    from oracle import align as OA
+    dims = W2vDims(name="t", n_layers=1, d_model=128, n_heads=2, ffn=256, vocab=32, conv_dim=64, pos_kernel=8, pos_groups=2)
+    sd = random_init_w2v(dims, seed=2)
+    eng = _OracleEngine(dims, sd)
+    model = AL.AlignModel(eng, dict(AL.DEFAULT_DICTIONARY), "en")
+    meta = {"language": "en", "dictionary": dict(AL.DEFAULT_DICTIONARY), "type": "b200"}
+    rng = np.random.default_rng(0)
+    audio = (rng.standard_normal(16000 * 10) * 0.1).astype(np.float32)
+    segs = [{"text": " one two", "start": 0.0, "end": 2.0}, {"text": "three", "start": 2.5, "end": 4.0},
+            {"text": "   ", "start": 4.0, "end": 4.5}, {"text": "four five six", "start": 5.0, "end": 9.5},
+            {"text": "x" * 40, "start": 9.6, "end": 9.7},                    # more characters than frames: not alignable
+            {"text": "gone", "start": 11.0, "end": 12.0}]                     # starts after the audio ends
+    res = AL.align(segs, model, meta, audio, "cpu", return_char_alignments=True, sentence_splitter=lambda t: [(0, len(t))])
+    assert eng.calls == [2, 2]                                                 # 4 alignable segments in batches of max_batch
+    out = res["segments"]
+    assert [s["text"] for s in out] == [s["text"] for s in segs]
+    assert [[w["word"] for w in s["words"]] for s in out] == [["one", "two"], ["three"], [], ["four", "five", "six"], [], []]
+    assert res["word_segments"] == [w for s in out for w in s["words"]]
+    printed = capsys.readouterr().out
+    assert printed.count("Failed to align segment") == 3
+    # the first segment, recomputed by hand from the oracle pieces
+    chars, cdx, toks = AL.preprocess_segment(segs[0]["text"], meta["dictionary"], "en")
+    with torch.no_grad():
+        e = eng.model.emissions(torch.from_numpy(audio[: 32000])).numpy()
+    merged = OA.merge_repeats(OA.backtrack(OA.get_trellis(e, toks, 0), e, toks, 0), "".join(chars))
+    ratio = 2.0 / (e.shape[0] - 1)
+    w0 = out[0]["words"][0]
+    assert w0["start"] == round(merged[0].start * ratio, 3) and w0["end"] == round(merged[2].end * ratio, 3)
+    assert w0["score"] == round(sum(round(m.score, 3) for m in merged[:3]) / 3, 3)
+    assert out[0]["chars"][1] == {"char": "o", "start": w0["start"], "end": round(merged[0].end * ratio, 3), "score": round(merged[0].score, 3)}
+    assert out[0]["start"] == w0["start"] and out[0]["end"] == out[0]["words"][-1]["end"]
