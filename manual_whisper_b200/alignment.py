@@ -97,6 +97,9 @@ class AlignEngine:
 
     def __init__(self, dims: W2vDims, sd: Dict[str, torch.Tensor], device_index: int = 0, max_batch: int = 16,
                  max_samples: int = 30 * SAMPLE_RATE):
+        if dims.feat_norm != "layer" or not dims.stable_layer_norm or not dims.conv_bias:
+            raise NotImplementedError("the CUDA alignment engine implements the layer-norm / stable-layer-norm wav2vec2 family "
+                                      "(XLSR-53); the group-norm wav2vec2-base variant is not built yet")
         if not torch.cuda.is_available():
             raise RuntimeError("manual_whisper_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()

@@ -26,6 +26,11 @@ class W2vDims:
     conv_stride: Tuple[int, ...] = (5, 2, 2, 2, 2, 2, 2)
     pos_kernel: int = 128
     pos_groups: int = 16
+    # "layer" + stable_layer_norm=True is the XLSR-53 family (what the CUDA engine implements); "group" + False + no conv
+    # bias is wav2vec2-base (whisperx's torchaudio models for en/fr/de/es/it) - oracle only so far
+    feat_norm: str = "layer"
+    stable_layer_norm: bool = True
+    conv_bias: bool = True
 
     def frames(self, n_samples: int) -> int:
         t = int(n_samples)
@@ -62,9 +67,11 @@ def random_init_w2v(dims: W2vDims, seed: int = 0, std: float = 0.05) -> Dict[str
     for i, k in enumerate(dims.conv_kernel):
         p = f"wav2vec2.feature_extractor.conv_layers.{i}"
         sd[p + ".conv.weight"] = rnd(dims.conv_dim, c_in, k, s=(2.0 / (c_in * k)) ** 0.5)
-        sd[p + ".conv.bias"] = rnd(dims.conv_dim, s=0.02)
-        sd[p + ".layer_norm.weight"] = 1.0 + rnd(dims.conv_dim, s=0.05)
-        sd[p + ".layer_norm.bias"] = rnd(dims.conv_dim, s=0.05)
+        if dims.conv_bias:
+            sd[p + ".conv.bias"] = rnd(dims.conv_dim, s=0.02)
+        if dims.feat_norm == "layer" or i == 0:
+            sd[p + ".layer_norm.weight"] = 1.0 + rnd(dims.conv_dim, s=0.05)
+            sd[p + ".layer_norm.bias"] = rnd(dims.conv_dim, s=0.05)
         c_in = dims.conv_dim
     sd["wav2vec2.feature_projection.layer_norm.weight"] = 1.0 + rnd(dims.conv_dim, s=0.05)
     sd["wav2vec2.feature_projection.layer_norm.bias"] = rnd(dims.conv_dim, s=0.05)

@@ -57,13 +57,17 @@ class OracleWav2Vec2:
     def features(self, wave: torch.Tensor) -> torch.Tensor:
         """[n_samples] -> [T, conv_dim]: 7 x (conv1d, LayerNorm over channels, GELU)  (modeling_wav2vec2.py:275-300)."""
         d = self.dims
+        group = getattr(d, "feat_norm", "layer") == "group"
         h = wave.view(1, 1, -1).float()
         for i, (k, s) in enumerate(zip(d.conv_kernel, d.conv_stride)):
             p = f"wav2vec2.feature_extractor.conv_layers.{i}"
             if i > 0:
                 h = _r(h, self.emu)          # the engine stores every conv layer's GELU output as bf16
-            h = F.conv1d(h, self.sd[p + ".conv.weight"], self.sd[p + ".conv.bias"], stride=s)
-            h = self._ln(h.transpose(1, 2), p + ".layer_norm").transpose(1, 2)
+            h = F.conv1d(h, self.sd[p + ".conv.weight"], self.sd.get(p + ".conv.bias"), stride=s)
+            if not group:
+                h = self._ln(h.transpose(1, 2), p + ".layer_norm").transpose(1, 2)
+            elif i == 0:     # wav2vec2-base: GroupNorm(C groups) = per-channel statistics over time, first layer only (:302-323)
+                h = F.group_norm(h, h.shape[1], self.sd[p + ".layer_norm.weight"], self.sd[p + ".layer_norm.bias"], 1e-5)
             h = F.gelu(h)
         return h[0].transpose(0, 1)
 
@@ -80,9 +84,12 @@ class OracleWav2Vec2:
         x = x + F.gelu(pos)[0].transpose(0, 1)
         T = x.shape[0]
         H, dh = d.n_heads, d.d_model // d.n_heads
+        stable = getattr(d, "stable_layer_norm", True)
+        if not stable:                                                           # post-LN encoder (:658-727): LN right after pos
+            x = self._ln(x, "wav2vec2.encoder.layer_norm")
         for l in range(d.n_layers):                                             # stable-layer-norm (pre-LN) layers, :612-655
             p = f"wav2vec2.encoder.layers.{l}"
-            y = self._ln(x, p + ".layer_norm")
+            y = self._ln(x, p + ".layer_norm") if stable else x
             q = _r(self._lin(y, p + ".attention.q_proj"), self.emu).view(T, H, dh).transpose(0, 1)
             k = _r(self._lin(y, p + ".attention.k_proj"), self.emu).view(T, H, dh).transpose(0, 1)
             v = _r(self._lin(y, p + ".attention.v_proj"), self.emu).view(T, H, dh).transpose(0, 1)
@@ -95,10 +102,15 @@ class OracleWav2Vec2:
                 o = torch.matmul(torch.softmax(s, dim=-1), v)
             o = o.transpose(0, 1).reshape(T, d.d_model)
             x = x + self._lin(o, p + ".attention.out_proj")
-            y = self._ln(x, p + ".final_layer_norm")
-            y = F.gelu(self._lin(y, p + ".feed_forward.intermediate_dense"))
-            x = x + self._lin(y, p + ".feed_forward.output_dense")
-        return self._ln(x, "wav2vec2.encoder.layer_norm")
+            if stable:
+                y = self._ln(x, p + ".final_layer_norm")
+                y = F.gelu(self._lin(y, p + ".feed_forward.intermediate_dense"))
+                x = x + self._lin(y, p + ".feed_forward.output_dense")
+            else:                                                                # :592-609: LN after each residual add
+                x = self._ln(x, p + ".layer_norm")
+                y = F.gelu(self._lin(x, p + ".feed_forward.intermediate_dense"))
+                x = self._ln(x + self._lin(y, p + ".feed_forward.output_dense"), p + ".final_layer_norm")
+        return self._ln(x, "wav2vec2.encoder.layer_norm") if stable else x
 
     def logits(self, wave: torch.Tensor) -> torch.Tensor:
         return self._lin(self.hidden(wave), "lm_head")

@@ -157,3 +157,10 @@ def test_align_control_flow_on_cpu_with_an_oracle_engine(capsys):
     assert w0["score"] == round(sum(round(m.score, 3) for m in merged[:3]) / 3, 3)
     assert out[0]["chars"][1] == {"char": "o", "start": w0["start"], "end": round(merged[0].end * ratio, 3), "score": round(merged[0].score, 3)}
     assert out[0]["start"] == w0["start"] and out[0]["end"] == out[0]["words"][-1]["end"]
+
+
+def test_engine_rejects_the_group_norm_variant_loudly():
+    from dataclasses import replace
+    base = replace(W2vDims(), feat_norm="group", stable_layer_norm=False, conv_bias=False)
+    with pytest.raises(NotImplementedError, match="group-norm"):
+        AL.AlignEngine(base, {}, device_index=0)

@@ -17,8 +17,8 @@ SMALL = W2vDims(name="w2v-test", n_layers=2, d_model=128, n_heads=2, ffn=256, vo
 def _hf_twin(dims, sd):
     from transformers import Wav2Vec2Config, Wav2Vec2ForCTC
     cfg = Wav2Vec2Config(vocab_size=dims.vocab, hidden_size=dims.d_model, num_hidden_layers=dims.n_layers,
-                         num_attention_heads=dims.n_heads, intermediate_size=dims.ffn, feat_extract_norm="layer",
-                         do_stable_layer_norm=True, conv_bias=True, conv_dim=[dims.conv_dim] * 7,
+                         num_attention_heads=dims.n_heads, intermediate_size=dims.ffn, feat_extract_norm=dims.feat_norm,
+                         do_stable_layer_norm=dims.stable_layer_norm, conv_bias=dims.conv_bias, conv_dim=[dims.conv_dim] * 7,
                          conv_kernel=list(dims.conv_kernel), conv_stride=list(dims.conv_stride),
                          num_conv_pos_embeddings=dims.pos_kernel, num_conv_pos_embedding_groups=dims.pos_groups,
                          hidden_act="gelu", feat_extract_activation="gelu", layer_norm_eps=1e-5)
@@ -60,6 +60,19 @@ def test_wav2vec2_oracle_matches_hf():
         assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
         with torch.no_grad():
             assert torch.allclose(ora.emissions(wave), torch.log_softmax(want, -1), atol=3e-4)
+
+
+def test_group_norm_base_variant_oracle_matches_hf():
+    """wav2vec2-base layout (GroupNorm on conv 0, no conv bias, post-LN encoder): oracle only, pinned for the next round."""
+    from dataclasses import replace
+    base = replace(SMALL, name="w2v-base-test", feat_norm="group", stable_layer_norm=False, conv_bias=False)
+    sd = random_init_w2v(base, seed=4)
+    hf = _hf_twin(base, sd)
+    ora = OracleWav2Vec2(base, sd)
+    wave = torch.randn(5000, generator=torch.Generator().manual_seed(1)) * 0.1
+    with torch.no_grad():
+        want, got = hf(wave[None]).logits[0], ora.logits(wave)
+    assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
 
 
 def test_pos_conv_weight_norm_forms():
