@@ -211,9 +211,12 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
         if sd is not None:
             n_layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("wav2vec2.encoder.layers."))
             d = sd["lm_head.weight"].shape[1]
+            fe = "wav2vec2.feature_extractor.conv_layers."
+            layer_norm_family = fe + "1.layer_norm.weight" in sd          # wav2vec2-base normalises conv layer 0 only
             dims = W2vDims(name=model_name or "checkpoint", n_layers=n_layers, d_model=d, n_heads=d // 64,
                            ffn=sd["wav2vec2.encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0],
-                           vocab=sd["lm_head.weight"].shape[0])
+                           vocab=sd["lm_head.weight"].shape[0], feat_norm="layer" if layer_norm_family else "group",
+                           stable_layer_norm=layer_norm_family, conv_bias=fe + "0.conv.bias" in sd)
         elif DEFAULT_ALIGN_DIMS is not None:
             dims = DEFAULT_ALIGN_DIMS
         else:
