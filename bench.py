@@ -14,6 +14,9 @@ owns its own recording (weak scaling, no data-path collective).
   e2e    = the same metric through the public API model.transcribe(host_audio, batch_size=32): pinned host
            waveform -> H2D -> windows -> ids back on the host, for the whole hour.
 
+--merge M (experiment, default 1) hands M user batches to the engine as one device batch of 32*M rows: rows are
+independent so results are unchanged; measured equal to the default within noise.
+
 --impl reference times the CPU restatement (oracle/) on the host cores on a bounded sample of the same
 workload (the reference's own CPU stack, whisperx/faster-whisper/CTranslate2, is not installable offline).
 """
