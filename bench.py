@@ -229,7 +229,7 @@ def main():
     pinned = torch.empty(len(audio_np), dtype=torch.float32, pin_memory=True)
     pinned.numpy()[:] = audio_np
     audio_host = pinned.numpy()
-    pipe = mw.load_model(MODEL, "cuda", device_index=local, compute_type="bfloat16", language="zh",
+    pipe = mw.load_model(MODEL, "cuda", device_index=local, compute_type="float16", language="zh",
                          asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), model=sd, max_batch=BATCH * args.merge,
                          streams_per_device=args.streams)
     del sd

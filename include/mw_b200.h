@@ -14,6 +14,7 @@
  *     (+) ctranslate2.models.Whisper.detect_language(enc)  [SURVEY §8(f) rank 2]   -> mw_detect_language
  *
  * Conventions
+ *   - "h16" below = the 16-bit storage type mw_storage_dtype() reports (fp16 unless built otherwise).
  *   - plain C types only; every pointer named d_* is DEVICE memory owned by the caller, h_* is host.
  *   - every call returns mw_status (0 = ok); the message is in mw_last_error() (thread-local).
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued there, no hidden sync unless stated.
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MW_ABI_VERSION 1
+#define MW_ABI_VERSION 2
 
 typedef int32_t mw_status;
 enum {
@@ -42,6 +43,10 @@ enum {
 };
 
 int mw_abi_version(void);
+/* 16-bit storage type of every "h16" buffer below (activations, K/V caches, weight matrices): 0 = IEEE fp16 (default:
+ * the reference's GPU compute_type "float16", /root/reference/transcribe_colab.ipynb:119), 1 = bf16 (library built with
+ * -DMW_STORAGE_BF16 for A/B runs).  Accumulation, residual stream, softmax statistics and logits are fp32 either way. */
+int mw_storage_dtype(void);
 const char* mw_last_error(void);
 /* number of kernels this library has launched since load (process-wide); bench.py's gpu_launches */
 uint64_t mw_launch_count(void);
@@ -57,7 +62,7 @@ void mw_logmel_plan_destroy(mw_logmel_plan* plan);
 
 /* The pipeline's per-chunk call: chunk c = d_audio[d_offsets[c] .. +d_lengths[c]) zero-padded to
  * 480000 samples, own global max.  d_out: float32 [n_chunks, n_mels, 3000].
- * d_out_t (may be NULL): additionally emits the bf16 time-major copy [n_chunks, 3002, n_mels]
+ * d_out_t (may be NULL): additionally emits the h16 time-major copy [n_chunks, 3002, n_mels]
  * (rows 0 and 3001 zero) that mw_encode's conv stem reads. */
 mw_status mw_logmel(mw_logmel_plan* plan, const float* d_audio, int64_t n_audio,
                     const int64_t* d_offsets, const int32_t* d_lengths, int n_chunks,
@@ -81,30 +86,30 @@ typedef struct mw_model_config {
 } mw_model_config;
 
 /* Weight table: device pointers in the order of enum mw_weight_id, then per-layer blocks.
- * Matrices are bf16 row-major [out, in] (torch Linear layout); vectors are fp32.  Pointers are
+ * Matrices are h16 row-major [out, in] (torch Linear layout); vectors are fp32.  Pointers are
  * BORROWED and must outlive the model.  Layouts the engine needs that differ from the checkpoint
  * (conv taps folded into K, q|k|v concatenated, zero k-bias) are prepared by the host shim
  * (manual_whisper_b200/engine.py: pack_weights). */
 enum mw_weight_id {
-    MW_W_CONV1 = 0,       /* bf16 [d, 3*n_mels]  k-major: [co][tap][ci] */
+    MW_W_CONV1 = 0,       /* h16 [d, 3*n_mels]  k-major: [co][tap][ci] */
     MW_B_CONV1,           /* f32  [d] */
-    MW_W_CONV2,           /* bf16 [d, 3*d]       [co][tap][ci] */
+    MW_W_CONV2,           /* h16 [d, 3*d]       [co][tap][ci] */
     MW_B_CONV2,           /* f32  [d] */
     MW_ENC_POS,           /* f32  [n_audio_ctx, d] */
     MW_ENC_LN_G, MW_ENC_LN_B,   /* f32 [d] final encoder LayerNorm */
-    MW_DEC_EMB,           /* bf16 [vocab, d] token embedding (tied output projection) */
+    MW_DEC_EMB,           /* h16 [vocab, d] token embedding (tied output projection) */
     MW_DEC_POS,           /* f32  [n_text_ctx, d] */
     MW_DEC_LN_G, MW_DEC_LN_B,   /* f32 [d] final decoder LayerNorm */
     MW_GLOBAL_COUNT
 };
 enum mw_enc_layer_weight_id {
     MW_EL_LN1_G = 0, MW_EL_LN1_B,
-    MW_EL_WQKV,           /* bf16 [3d, d]   q|k|v rows */
+    MW_EL_WQKV,           /* h16 [3d, d]   q|k|v rows */
     MW_EL_BQKV,           /* f32  [3d]      k part zero */
-    MW_EL_WO, MW_EL_BO,   /* bf16 [d, d], f32 [d] */
+    MW_EL_WO, MW_EL_BO,   /* h16 [d, d], f32 [d] */
     MW_EL_LN2_G, MW_EL_LN2_B,
-    MW_EL_W1, MW_EL_B1,   /* bf16 [ffn, d], f32 [ffn] */
-    MW_EL_W2, MW_EL_B2,   /* bf16 [d, ffn], f32 [d] */
+    MW_EL_W1, MW_EL_B1,   /* h16 [ffn, d], f32 [ffn] */
+    MW_EL_W2, MW_EL_B2,   /* h16 [d, ffn], f32 [d] */
     MW_EL_COUNT
 };
 enum mw_dec_layer_weight_id {
@@ -112,8 +117,8 @@ enum mw_dec_layer_weight_id {
     MW_DL_WQKV, MW_DL_BQKV,
     MW_DL_WO, MW_DL_BO,
     MW_DL_LNX_G, MW_DL_LNX_B,   /* encoder_attn_layer_norm */
-    MW_DL_WXQ, MW_DL_BXQ,       /* cross q: bf16 [d,d], f32 [d] */
-    MW_DL_WXKV, MW_DL_BXKV,     /* cross k|v: bf16 [2d,d], f32 [2d] (k part zero) */
+    MW_DL_WXQ, MW_DL_BXQ,       /* cross q: h16 [d,d], f32 [d] */
+    MW_DL_WXKV, MW_DL_BXKV,     /* cross k|v: h16 [2d,d], f32 [2d] (k part zero) */
     MW_DL_WXO, MW_DL_BXO,
     MW_DL_LN2_G, MW_DL_LN2_B,
     MW_DL_W1, MW_DL_B1,
@@ -130,9 +135,9 @@ void mw_model_destroy(mw_model* model);
 /* bytes of device workspace the model allocated at create */
 int64_t mw_model_workspace_bytes(const mw_model* model);
 
-/* S2. d_mel: float32 [B, n_mels, 3000]; d_enc_out: bf16 [B, n_audio_ctx, d_model]. */
+/* S2. d_mel: float32 [B, n_mels, 3000]; d_enc_out: h16 [B, n_audio_ctx, d_model]. */
 mw_status mw_encode(mw_model* model, const float* d_mel, int B, void* d_enc_out, void* stream);
-/* Same, reading the bf16 time-major features mw_logmel emitted ([B, 3002, n_mels]). */
+/* Same, reading the h16 time-major features mw_logmel emitted ([B, 3002, n_mels]). */
 mw_status mw_encode_t(mw_model* model, const void* d_mel_t, int B, void* d_enc_out, void* stream);
 
 typedef struct mw_gen_options {
@@ -153,7 +158,7 @@ typedef struct mw_gen_options {
     int32_t forced_eot_len;       /* bench-only knob: >0 forces <eot> after this many tokens; 0 = off */
 } mw_gen_options;
 
-/* S3.  d_enc: bf16 [B, n_audio_ctx, d_model].  One shared prompt (whisperx passes [prompt]*B).
+/* S3.  d_enc: h16 [B, n_audio_ctx, d_model].  One shared prompt (whisperx passes [prompt]*B).
  * h_out_ids: host int32 [B, num_hypotheses, max_new] (max_new = min(max_length/2, max_length-prompt_len)),
  * h_out_len: host int32 [B, num_hypotheses], h_out_scores: host float [B, num_hypotheses].
  * Synchronises `stream` before returning (ids are returned to the host, like CT2). */
@@ -171,12 +176,12 @@ mw_status mw_detect_language(mw_model* model, const void* d_enc, int B, int32_t 
 
 /* ------------------------------------------------------------------ building blocks ------------
  * Exposed so tests can pin each kernel against torch on its own (tests/test_gpu_kernels.py). */
-/* D[M,N] = A[M,K] . W[N,K]^T (+bias[N]) (gelu) (+residual f32[M,N]); A,W bf16; out bf16 or f32. */
-mw_status mw_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, const float* d_residual,
+/* D[M,N] = A[M,K] . W[N,K]^T (+bias[N]) (gelu) (+residual f32[M,N]); A,W h16; out h16 or f32. */
+mw_status mw_gemm_h16(const void* d_a, const void* d_w, const float* d_bias, const float* d_residual,
                        void* d_out, int M, int N, int K, int gelu, int out_f32, void* stream);
-/* encoder self-attention on packed qkv bf16 [B*T, 3*d]; out bf16 [B*T, d] */
-mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream);
-mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_bf16,
+/* encoder self-attention on packed qkv h16 [B*T, 3*d]; out h16 [B*T, d] */
+mw_status mw_attention_h16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream);
+mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_h16,
                        int rows, int d, void* stream);
 
 /* VAD front end: RMS of consecutive frames of `frame` samples, d_out float32 [n / frame].
@@ -211,18 +216,18 @@ typedef struct mw_w2v_config {
 } mw_w2v_config;
 
 /* Weight table: MW_A_* globals, then n_layers blocks in the order of enum mw_enc_layer_weight_id (q|k|v rows
- * concatenated, all three biases real).  Matrices bf16 row-major [out, in]; vectors fp32; pointers borrowed. */
+ * concatenated, all three biases real).  Matrices h16 row-major [out, in]; vectors fp32; pointers borrowed. */
 enum mw_w2v_weight_id {
     MW_A_CONV0_W = 0,     /* f32 [conv_dim, 10] */
     MW_A_CONV0_B, MW_A_CONV0_LN_G, MW_A_CONV0_LN_B,
-    MW_A_CONV1_W,         /* conv layer i = 1..6 at MW_A_CONV0_W + 4 i: bf16 [conv_dim, k_i * conv_dim] as [co][tap][ci], */
+    MW_A_CONV1_W,         /* conv layer i = 1..6 at MW_A_CONV0_W + 4 i: h16 [conv_dim, k_i * conv_dim] as [co][tap][ci], */
     MW_A_CONV1_B, MW_A_CONV1_LN_G, MW_A_CONV1_LN_B,   /* then bias, LayerNorm gamma, beta */
     MW_A_FP_LN_G = 28, MW_A_FP_LN_B,   /* feature_projection.layer_norm */
-    MW_A_FP_W, MW_A_FP_B,              /* feature_projection.projection: bf16 [d, conv_dim], f32 [d] */
-    MW_A_POS_W,           /* bf16 [groups][64 out][pos_kernel taps][64 in]: effective (weight-normalised) pos-conv weight */
+    MW_A_FP_W, MW_A_FP_B,              /* feature_projection.projection: h16 [d, conv_dim], f32 [d] */
+    MW_A_POS_W,           /* h16 [groups][64 out][pos_kernel taps][64 in]: effective (weight-normalised) pos-conv weight */
     MW_A_POS_B,           /* f32 [d] */
     MW_A_ENC_LN_G, MW_A_ENC_LN_B,      /* encoder.layer_norm (after the last layer) */
-    MW_A_LM_W, MW_A_LM_B,              /* lm_head: bf16 [ceil32(vocab), d], f32 [ceil32(vocab)] */
+    MW_A_LM_W, MW_A_LM_B,              /* lm_head: h16 [ceil32(vocab), d], f32 [ceil32(vocab)] */
     MW_A_GLOBAL_COUNT
 };
 

@@ -47,6 +47,7 @@ class WeightTableC(C.Structure):
 # tests/test_abi.py checks the library exports each of them.
 SIGNATURES = {
     "mw_abi_version": (C.c_int, []),
+    "mw_storage_dtype": (C.c_int, []),
     "mw_last_error": (C.c_char_p, []),
     "mw_launch_count": (C.c_uint64, []),
     "mw_logmel_plan_create": (C.c_int32, [C.c_int, c_f32p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -64,9 +65,9 @@ SIGNATURES = {
     "mw_decoder_logits": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.c_int, C.c_void_p, C.c_void_p]),
     "mw_detect_language": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32,
                                        c_f32p, C.c_void_p]),
-    "mw_gemm_bf16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+    "mw_gemm_h16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "mw_attention_bf16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mw_attention_h16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mw_bench_kernel": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "mw_bench_step": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "mw_frame_rms": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
@@ -102,8 +103,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mw_abi_version() != 1:
-        raise RuntimeError(f"libmw_b200.so ABI version {lib.mw_abi_version()} != 1")
+    if lib.mw_abi_version() != 2:
+        raise RuntimeError(f"libmw_b200.so ABI version {lib.mw_abi_version()} != 2 (rebuild: python -m manual_whisper_b200.build)")
     _lib = lib
     return lib
 
@@ -114,6 +115,13 @@ def check(status: int, what: str):
         if status == 1:
             raise ValueError(f"{what}: {msg}")
         raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def storage_dtype():
+    """torch dtype of the engine's 16-bit buffers (include/mw_b200.h: mw_storage_dtype): float16 unless the library was
+    built with MW_STORAGE_BF16=1."""
+    import torch
+    return torch.bfloat16 if load().mw_storage_dtype() == 1 else torch.float16
 
 
 def launch_count() -> int:

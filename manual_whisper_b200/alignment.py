@@ -50,7 +50,7 @@ def pack_w2v_weights(sd: Dict[str, torch.Tensor], dims: W2vDims, device: torch.d
     """Hugging Face ``Wav2Vec2ForCTC`` state dict -> the engine's weight table (order of enum mw_w2v_weight_id, then the
     per-layer blocks of enum mw_enc_layer_weight_id)."""
     def mat(t):
-        return t.to(device=device, dtype=torch.bfloat16).contiguous()
+        return t.to(device=device, dtype=_lib.storage_dtype()).contiguous()
 
     def vec(t):
         return t.to(device=device, dtype=torch.float32).contiguous()

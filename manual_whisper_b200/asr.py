@@ -110,7 +110,7 @@ class WhisperModel:
         self.feat_kwargs = {"feature_size": dims.n_mels}
         self.is_multilingual = True
         self.plan = _audio.LogMelPlan(dims.n_mels, self.device, max_chunks=max_batch)
-        self._feat_t = torch.empty((max_batch, N_FRAMES + 2, dims.n_mels), dtype=torch.bfloat16, device=self.device)
+        self._feat_t = torch.empty((max_batch, N_FRAMES + 2, dims.n_mels), dtype=self.engine.h16, device=self.device)
         self._feat = torch.empty((max_batch, dims.n_mels, N_FRAMES), dtype=torch.float32, device=self.device)
 
     @property
@@ -386,7 +386,7 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
     Arguments up to ``threads`` are whisperx's.  ``device`` must be "cuda": the shipped
     reference sets DEVICE="cpu" (/root/reference/transcribe.py:30) and tells GPU users to change that
     constant (/root/reference/README.md:101) — there is no CPU path here.  ``compute_type`` is accepted for
-    signature parity; the engine always computes in bf16 with fp32 accumulation.  ``model`` may be a ready
+    signature parity; the engine always computes on fp16 storage (the reference's GPU compute type, /root/reference/transcribe_colab.ipynb:119) with fp32 accumulation.  ``model`` may be a ready
     WhisperModel, an HF-named state dict, or the path of a Hugging Face ``model.safetensors`` (also looked up under
     ``download_root``); with none of these, seeded random-init weights are used because no checkpoint can be downloaded
     offline (a warning says so).  Keyword-only arguments are additions;
@@ -399,8 +399,8 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
         raise ValueError(f"unsupported device {device!r}: the B200-native engine has no CPU path; pass device='cuda'")
     if compute_type not in _COMPUTE_TYPES:
         raise ValueError(f"Requested compute type {compute_type!r} is not a valid compute type")
-    if compute_type not in ("bfloat16", "default", "auto"):
-        warnings.warn(f"compute_type={compute_type!r} requested; the sm_100a engine computes in bfloat16 with fp32 accumulation")
+    if compute_type not in ("float16", "bfloat16", "default", "auto"):
+        warnings.warn(f"compute_type={compute_type!r} requested; the sm_100a engine computes on 16-bit storage (float16) with fp32 accumulation")
     if vad_model is None and vad_method not in ("pyannote", "silero", "energy", "energy_gpu", None):
         raise ValueError(f"Invalid vad_method: {vad_method}")
     mdims = dims or model_dims(whisper_arch)

@@ -208,7 +208,7 @@ class LogMelPlan:
         assert offsets.dtype == torch.int64 and lengths.dtype == torch.int32
         assert out.is_contiguous() and out.shape == (n, self.n_mels, N_FRAMES)
         if out_t is not None:
-            assert out_t.dtype == torch.bfloat16 and out_t.is_contiguous()
+            assert out_t.dtype == _lib.storage_dtype() and out_t.is_contiguous()
             assert out_t.shape == (n, N_FRAMES + 2, self.n_mels)
         _lib.check(self.lib.mw_logmel(self.handle, audio.data_ptr(), audio.numel(), offsets.data_ptr(),
                                       lengths.data_ptr(), n, out.data_ptr(),

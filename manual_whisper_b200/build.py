@@ -40,8 +40,15 @@ def _newest_header() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """MW_STORAGE_BF16=1 in the environment builds the bf16-storage variant (A/B runs; default is fp16)."""
     nvcc = _nvcc()
     OBJ.mkdir(parents=True, exist_ok=True)
+    variant = "bf16" if os.environ.get("MW_STORAGE_BF16") == "1" else "fp16"
+    stamp = OBJ / "variant.txt"
+    if not stamp.exists() or stamp.read_text() != variant:
+        force = True
+        stamp.write_text(variant)
+    extra = ["-DMW_STORAGE_BF16"] if variant == "bf16" else []
     srcs = sorted(CSRC.glob("*.cu"))
     hdr = max(_newest_header(), Path(__file__).stat().st_mtime)
     jobs = []
@@ -52,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(s), "-o", str(o)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ / (s.stem + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:

@@ -36,7 +36,7 @@ __device__ __forceinline__ float ex2(float x) {
 // serves the others, which is what hides the MMA / mbarrier / tcgen05.ld latencies of the serial per-block chain.
 __global__ void __launch_bounds__(128, 3)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                         __nv_bfloat16* __restrict__ out, int Tq, int Tk_max, int colq0, int colk0, int colv0, int out_ld,
+                         mw_h* __restrict__ out, int Tq, int Tk_max, int colq0, int colk0, int colv0, int out_ld,
                          float scale_log2e, const int* __restrict__ kv_lens) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,8 +90,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tma_load_3d(sV, &tmap_kv, bar_v, col_v, 0, b);
     }
 
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, TK, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, DH, 1);   // B (=V) is MN-major
+    constexpr uint32_t idesc_s = make_idesc_h16(128, TK, 0);
+    constexpr uint32_t idesc_o = make_idesc_h16(128, DH, 1);   // B (=V) is MN-major
 
     float acc[DH];
 #pragma unroll
@@ -106,7 +106,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             const uint64_t dq = make_desc_sw128(smem_u32(sQ), 1024, 0);
             const uint64_t dk = make_desc_sw128(smem_u32(sK), 1024, 0);
 #pragma unroll
-            for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+            for (int k = 0; k < DH / 16; ++k) umma_h16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
             umma_commit(bar_s);
         }
         __syncwarp();
@@ -151,7 +151,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const float p0 = ex2(fmaf(__uint_as_float(half ? r1[i] : r0[i]), scale_log2e, -mb));
                 const float p1 = ex2(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), scale_log2e, -mb));
                 if (i & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
-                __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                mw_h2 hh = f2h2(p0, p1);
                 packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
             }
 #pragma unroll
@@ -174,7 +174,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             for (int k = 0; k < TK / 16; ++k) {
                 const uint64_t dp = make_desc_sw128(smem_u32(sP) + k * 32, 1024, 0);
                 const uint64_t dv = make_desc_sw128(smem_u32(sV) + k * 2048, 1024, KV_BYTES);
-                umma_bf16(tmem_o, dp, dv, idesc_o, k ? 1u : 0u);
+                umma_h16(tmem_o, dp, dv, idesc_o, k ? 1u : 0u);
             }
             umma_commit(bar_o);
         }
@@ -206,7 +206,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 hh = __floats2bfloat162_rn(acc[8 * g + 2 * i] * inv, acc[8 * g + 2 * i + 1] * inv);
+                mw_h2 hh = f2h2(acc[8 * g + 2 * i] * inv, acc[8 * g + 2 * i + 1] * inv);
                 w[i] = *reinterpret_cast<uint32_t*>(&hh);
             }
             o4[g] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -248,7 +248,7 @@ mw_status attention_launch_general(const void* d_q, int64_t ldq, int colq0, cons
     MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM); }));
     dim3 grid(ceil_div(Tq, TQ), n_heads, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;   // d_head^-0.5 * log2(e)
-    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (__nv_bfloat16*)d_out, Tq, Tk, colq0, colk0, colv0, out_ld,
+    attention_tcgen05_kernel<<<grid, 128, ATT_SMEM, st>>>(tm_q, tm_kv, (mw_h*)d_out, Tq, Tk, colq0, colk0, colv0, out_ld,
                                                           scale_log2e, d_kv_lens);
     MW_LAUNCH_CHECK();
     return MW_OK;
@@ -261,6 +261,6 @@ mw_status attention_launch(const void* d_qkv, void* d_out, int B, int T, int n_h
 
 }  // namespace mw
 
-extern "C" mw_status mw_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream) {
+extern "C" mw_status mw_attention_h16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream) {
     return mw::attention_launch(d_qkv, d_out, B, T, n_heads, (cudaStream_t)stream, nullptr);
 }

@@ -43,15 +43,15 @@ constexpr int NCAND = 2 * MAX_BEAM;
 
 struct DecoderState {
     int R_max = 0, max_new = 0;
-    __nv_bfloat16* kv_cross = nullptr;   // [L][B*T][2d]
-    __nv_bfloat16* k_self = nullptr;     // [L][R][ctx][d]
-    __nv_bfloat16* v_self = nullptr;
+    mw_h* kv_cross = nullptr;   // [L][B*T][2d]
+    mw_h* k_self = nullptr;     // [L][R][ctx][d]
+    mw_h* v_self = nullptr;
     float* x = nullptr;                  // [R, d]
-    __nv_bfloat16* ln = nullptr;         // [R, d]
-    __nv_bfloat16* qkv = nullptr;        // [R, 3d]
-    __nv_bfloat16* qx = nullptr;         // [R, d]
-    __nv_bfloat16* att = nullptr;        // [R, d]
-    __nv_bfloat16* mlp = nullptr;        // [R, ffn]
+    mw_h* ln = nullptr;         // [R, d]
+    mw_h* qkv = nullptr;        // [R, 3d]
+    mw_h* qx = nullptr;         // [R, d]
+    mw_h* att = nullptr;        // [R, d]
+    mw_h* mlp = nullptr;        // [R, ffn]
     float* logits = nullptr;             // [R, V]
     int* cur_tok = nullptr;              // [R]
     mw::DecCtl* ctl = nullptr;
@@ -98,10 +98,10 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_FLAG_GELU = 1, SK_FLAG_F32 = 2;
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+__device__ __forceinline__ void mma_h16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32." MW_MMA_SYNC_TYPE "." MW_MMA_SYNC_TYPE ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -114,16 +114,16 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 }
 
 __global__ void __launch_bounds__(256)
-skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+skinny_gemm_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                    const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                    int flags) {
     __shared__ float red[8][32][17];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int n0 = blockIdx.x * 16, r0 = blockIdx.y * 32;
-    const __nv_bfloat16* wa = W + (int64_t)min(n0 + g, N - 1) * ldw + q * 8;
-    const __nv_bfloat16* wb = W + (int64_t)min(n0 + g + 8, N - 1) * ldw + q * 8;
-    const __nv_bfloat16* xr[4];
+    const mw_h* wa = W + (int64_t)min(n0 + g, N - 1) * ldw + q * 8;
+    const mw_h* wb = W + (int64_t)min(n0 + g + 8, N - 1) * ldw + q * 8;
+    const mw_h* xr[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xr[t] = X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + q * 8;
     float c[4][4];
@@ -142,8 +142,8 @@ skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bflo
         for (int t = 0; t < 4; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(xr[t] + k));
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            mma_bf16_16816(c[t], alo.x, ahi.x, alo.y, ahi.y, b[t].x, b[t].y);
-            mma_bf16_16816(c[t], alo.z, ahi.z, alo.w, ahi.w, b[t].z, b[t].w);
+            mma_h16_16816(c[t], alo.x, ahi.x, alo.y, ahi.y, b[t].x, b[t].y);
+            mma_h16_16816(c[t], alo.z, ahi.z, alo.w, ahi.w, b[t].z, b[t].w);
         }
     }
 #pragma unroll
@@ -167,7 +167,7 @@ skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bflo
             const int64_t oi = (int64_t)r * ldo + n;
             if (resid) v += resid[oi];
             if (flags & SK_FLAG_F32) reinterpret_cast<float*>(out)[oi] = v;
-            else reinterpret_cast<__nv_bfloat16*>(out)[oi] = __float2bfloat16(v);
+            else reinterpret_cast<mw_h*>(out)[oi] = f2h(v);
         }
     }
 }
@@ -177,7 +177,7 @@ skinny_gemm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bflo
 // anything else, so a kernel's whole matrix is in flight at once.
 template <int KB, int NW, int WT>
 __global__ void __launch_bounds__(NW * 32, WT == 2 ? 2 : 1)
-skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+skinny_gemm_rows16_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                           const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                           int flags) {
     // WT = 16-row weight tiles per CTA.  Every CTA re-reads the whole X block [32, K] from L2, so with one tile the L2->SM
@@ -190,15 +190,15 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
     uint4 alo[WT][KB], ahi[WT][KB];
 #pragma unroll
     for (int wt = 0; wt < WT; ++wt) {
-        const __nv_bfloat16* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
-        const __nv_bfloat16* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
+        const mw_h* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
+        const mw_h* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
 #pragma unroll
         for (int i = 0; i < KB; ++i) {
             alo[wt][i] = ldg_stream(wa + i * 32);
             ahi[wt][i] = ldg_stream(wb + i * 32);
         }
     }
-    const __nv_bfloat16* xr[4];
+    const mw_h* xr[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xr[t] = X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + k_start;
     float c[WT][4][4];
@@ -217,8 +217,8 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
         for (int wt = 0; wt < WT; ++wt)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                mma_bf16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
-                mma_bf16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
+                mma_h16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
+                mma_h16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
             }
     }
 #pragma unroll
@@ -243,7 +243,7 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
             const int64_t oi = (int64_t)r * ldo + n;
             if (resid) v += resid[oi];
             if (flags & SK_FLAG_F32) reinterpret_cast<float*>(out)[oi] = v;
-            else reinterpret_cast<__nv_bfloat16*>(out)[oi] = __float2bfloat16(v);
+            else reinterpret_cast<mw_h*>(out)[oi] = f2h(v);
         }
     }
 }
@@ -252,7 +252,7 @@ skinny_gemm_rows16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __
 // KB blocks per warp (weights of one half in flight at a time) and the 16 warps reduce through 8 shared-memory slots.
 template <int KB, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-skinny_gemm_rows32_khalf_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                                 const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                                 int flags) {
     static_assert(NW == 16, "two rounds through 8 reduction slots");
@@ -274,8 +274,8 @@ skinny_gemm_rows32_khalf_kernel(const __nv_bfloat16* __restrict__ X, int ldx, co
         uint4 alo[WT][KB], ahi[WT][KB];
 #pragma unroll
         for (int wt = 0; wt < WT; ++wt) {
-            const __nv_bfloat16* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
-            const __nv_bfloat16* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
+            const mw_h* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
+            const mw_h* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
 #pragma unroll
             for (int i = 0; i < KB; ++i) {
                 alo[wt][i] = ldg_stream(wa + i * 32);
@@ -292,8 +292,8 @@ skinny_gemm_rows32_khalf_kernel(const __nv_bfloat16* __restrict__ X, int ldx, co
             for (int wt = 0; wt < WT; ++wt)
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    mma_bf16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
-                    mma_bf16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
+                    mma_h16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
+                    mma_h16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
                 }
         }
     }
@@ -326,7 +326,7 @@ skinny_gemm_rows32_khalf_kernel(const __nv_bfloat16* __restrict__ X, int ldx, co
             const int64_t oi = (int64_t)r * ldo + n;
             if (resid) v += resid[oi];
             if (flags & SK_FLAG_F32) reinterpret_cast<float*>(out)[oi] = v;
-            else reinterpret_cast<__nv_bfloat16*>(out)[oi] = __float2bfloat16(v);
+            else reinterpret_cast<mw_h*>(out)[oi] = f2h(v);
         }
     }
 }
@@ -340,7 +340,7 @@ mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const fl
         static const bool no_khalf = [] { const char* e = getenv("MW_SKINNY_KHALF"); return e && e[0] == '0'; }();
         if (!one_tile && !no_khalf) {
             dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
-            skinny_gemm_rows32_khalf_kernel<KB / 2, NW><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W,
+            skinny_gemm_rows32_khalf_kernel<KB / 2, NW><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W,
                                                                                   ldw, bias, resid, out, ldo, R, N, K, flags);
             MW_LAUNCH_CHECK();
             return MW_OK;
@@ -348,11 +348,11 @@ mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const fl
     }
     if (WT == 2 && !one_tile) {
         dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
-        skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw,
+        skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw,
                                                                         bias, resid, out, ldo, R, N, K, flags);
     } else {
         dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
-        skinny_gemm_rows16_kernel<KB, NW, 1><<<grid, NW * 32, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw,
+        skinny_gemm_rows16_kernel<KB, NW, 1><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw,
                                                                        bias, resid, out, ldo, R, N, K, flags);
     }
     MW_LAUNCH_CHECK();
@@ -376,31 +376,31 @@ mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const floa
     MW_SK(1, 8);    // 256
 #undef MW_SK
     dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
-    skinny_gemm_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)W, ldw, bias, resid,
+    skinny_gemm_kernel<<<grid, 256, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw, bias, resid,
                                              out, ldo, R, N, K, flags);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void embed_kernel(const int* __restrict__ cur_tok, const __nv_bfloat16* __restrict__ emb,
+__global__ void embed_kernel(const int* __restrict__ cur_tok, const mw_h* __restrict__ emb,
                              const float* __restrict__ pos_emb, const DecCtl* __restrict__ ctl, float* __restrict__ x, int d) {
     const int r = blockIdx.x;
     const int tok = cur_tok[r];
     const int pos = ctl->pos;
     for (int i = threadIdx.x; i < d; i += blockDim.x)
-        x[(int64_t)r * d + i] = __bfloat162float(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
+        x[(int64_t)r * d + i] = h2f(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
 }
 
 // ------------------------------------------------------------------------------------------------
 // decode attention: one CTA (128 threads) per (head, row); keys streamed once, 16 bytes per lane,
 // 8 lanes per key.  SELF: appends this step's k,v to the cache first and reads pos+1 keys.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+__device__ __forceinline__ void h16x8_to_float(const uint4& u, float (&f)[8]) {
+    const mw_h2* h = reinterpret_cast<const mw_h2*>(&u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 t = __bfloat1622float2(h[i]);
+        const float2 t = h22f2(h[i]);
         f[2 * i] = t.x;
         f[2 * i + 1] = t.y;
     }
@@ -408,11 +408,11 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
 
 template <bool SELF>
 __global__ void __launch_bounds__(128)
-decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
-                   __nv_bfloat16* kbase, __nv_bfloat16* vbase, int64_t key_stride, int64_t keys_per_seq,
+decode_attn_kernel(const mw_h* __restrict__ q, int ldq,
+                   mw_h* kbase, mw_h* vbase, int64_t key_stride, int64_t keys_per_seq,
                    const int* __restrict__ idx_table, int ctx, const DecCtl* __restrict__ ctl, int n_keys_fixed,
-                   int rows_per_seq, const __nv_bfloat16* __restrict__ knew, const __nv_bfloat16* __restrict__ vnew,
-                   int ld_new, __nv_bfloat16* __restrict__ out, int ldo, int causal_rows = 0) {
+                   int rows_per_seq, const mw_h* __restrict__ knew, const mw_h* __restrict__ vnew,
+                   int ld_new, mw_h* __restrict__ out, int ldo, int causal_rows = 0) {
     extern __shared__ float sc[];          // scores [n_keys] + reduction scratch
     __shared__ float red[4][64];
     __shared__ float red_s[8];
@@ -429,8 +429,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
         // append this row's k, v at position pos into its own physical cache row
         if (tid < 16) {
             const int part = tid >> 3, c8 = tid & 7;
-            const __nv_bfloat16* src = (part ? vnew : knew) + (int64_t)r * ld_new + h * 64 + c8 * 8;
-            __nv_bfloat16* dst = (part ? vbase : kbase) + ((int64_t)r * keys_per_seq + pos) * key_stride + h * 64 + c8 * 8;
+            const mw_h* src = (part ? vnew : knew) + (int64_t)r * ld_new + h * 64 + c8 * 8;
+            mw_h* dst = (part ? vbase : kbase) + ((int64_t)r * keys_per_seq + pos) * key_stride + h * 64 + c8 * 8;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
         }
         __syncthreads();
@@ -439,7 +439,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     float qf[8];
     {
         const uint4 u = *reinterpret_cast<const uint4*>(q + (int64_t)r * ldq + h * 64 + lg * 8);
-        bf16x8_to_float(u, qf);
+        h16x8_to_float(u, qf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) qf[i] *= 0.125f;
     }
@@ -462,7 +462,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
             float s = 0.0f;
             if (key < n_keys) {
                 float kf[8];
-                bf16x8_to_float(kv[u], kf);
+                h16x8_to_float(kv[u], kf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s = fmaf(qf[i], kf[i], s);
             }
@@ -512,7 +512,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
             if (key < n_keys) {
                 const float p = sc[key];
                 float vf[8];
-                bf16x8_to_float(vv[u], vf);
+                h16x8_to_float(vv[u], vf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
             }
@@ -530,7 +530,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
     __syncthreads();
     if (tid < 64) {
         const float v = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) / sum;
-        out[(int64_t)r * ldo + h * 64 + tid] = __float2bfloat16(v);
+        out[(int64_t)r * ldo + h * 64 + tid] = f2h(v);
     }
 }
 
@@ -542,9 +542,9 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
 // decode_attn_kernel: 16 bytes per lane, 8 lanes per key, 4 keys per warp instruction.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
-                         const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
-                         __nv_bfloat16* __restrict__ out, int ldo) {
+cross_attn_stream_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __restrict__ kbase,
+                         const mw_h* __restrict__ vbase, int64_t key_stride, int n_keys,
+                         mw_h* __restrict__ out, int ldo) {
     __shared__ float part_acc[16][64];
     __shared__ float part_m[16], part_l[16];
     constexpr int UNR = 4;
@@ -552,12 +552,12 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
     const int key_lo = 0, key_hi = n_keys;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lg = lane & 7, kq = lane >> 3;
-    const __nv_bfloat16* kp = kbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
-    const __nv_bfloat16* vp = vbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
+    const mw_h* kp = kbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
+    const mw_h* vp = vbase + (int64_t)r * n_keys * key_stride + h * 64 + lg * 8;
     float qf[8];
     {
         const uint4 u = *reinterpret_cast<const uint4*>(q + (int64_t)r * ldq + h * 64 + lg * 8);
-        bf16x8_to_float(u, qf);
+        h16x8_to_float(u, qf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) qf[i] *= 0.125f;
     }
@@ -581,7 +581,7 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
             sv[u] = 0.0f;
             if (key0 + 16 * u < key_hi) {
                 float kf[8];
-                bf16x8_to_float(kv[u], kf);
+                h16x8_to_float(kv[u], kf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sv[u] = fmaf(qf[i], kf[i], sv[u]);
             }
@@ -606,7 +606,7 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
                 const float p = __expf(sc - m);
                 l += p;
                 float vf[8];
-                bf16x8_to_float(vv[u], vf);
+                h16x8_to_float(vv[u], vf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
             }
@@ -628,7 +628,7 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
             num = fmaf(w, part_acc[g][tid], num);
             den = fmaf(w, part_l[g], den);
         }
-        out[(int64_t)r * ldo + h * 64 + tid] = __float2bfloat16(num / den);
+        out[(int64_t)r * ldo + h * 64 + tid] = f2h(num / den);
     }
 }
 
@@ -639,9 +639,9 @@ cross_attn_stream_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __n
 // ------------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(128, 5)
-cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kbase,
-                          const __nv_bfloat16* __restrict__ vbase, int64_t key_stride, int n_keys,
-                          __nv_bfloat16* __restrict__ out, int ldo) {
+cross_attn_grouped_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __restrict__ kbase,
+                          const mw_h* __restrict__ vbase, int64_t key_stride, int n_keys,
+                          mw_h* __restrict__ out, int ldo) {
     extern __shared__ float sc[];          // [G][n_keys] scores, then probabilities
     __shared__ float red[4][G][64];
     __shared__ float red_s[G][8];
@@ -653,12 +653,12 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const uint4 u = *reinterpret_cast<const uint4*>(q + (int64_t)(b * G + g) * ldq + h * 64 + lg * 8);
-        bf16x8_to_float(u, qf[g]);
+        h16x8_to_float(u, qf[g]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) qf[g][i] *= 0.125f;
     }
-    const __nv_bfloat16* kb = kbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
-    const __nv_bfloat16* vb = vbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
+    const mw_h* kb = kbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
+    const mw_h* vb = vbase + (int64_t)b * n_keys * key_stride + h * 64 + lg * 8;
     // Scores: every lane forms 8-dim partial dots for all G queries; a 3-round reduce-scatter over the 8 lanes of a key
     // (4 + 2 + 1 shuffles instead of 3 per query) leaves lane lg with the complete score of query lg.
     const bool b2 = lg & 4, b1 = lg & 2, b0 = lg & 1;
@@ -679,7 +679,7 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
             for (int g = 0; g < 8; ++g) v[g] = 0.0f;
             if (key < n_keys) {
                 float kf[8];
-                bf16x8_to_float(kv[u], kf);
+                h16x8_to_float(kv[u], kf);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -744,7 +744,7 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
             const int key = key0 + 16 * u;
             if (key < n_keys) {
                 float vf[8];
-                bf16x8_to_float(vv[u], vf);
+                h16x8_to_float(vv[u], vf);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const float p = sc[g * n_keys + key];
@@ -770,13 +770,13 @@ cross_attn_grouped_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
     for (int o = tid; o < G * 64; o += 128) {
         const int g = o >> 6, dcol = o & 63;
         const float v = ((red[0][g][dcol] + red[1][g][dcol]) + (red[2][g][dcol] + red[3][g][dcol])) / ((red_s[g][4] + red_s[g][5]) + (red_s[g][6] + red_s[g][7]));
-        out[(int64_t)(b * G + g) * ldo + h * 64 + dcol] = __float2bfloat16(v);
+        out[(int64_t)(b * G + g) * ldo + h * 64 + dcol] = f2h(v);
     }
 }
 
 template <int G>
-mw_status launch_cross_grouped(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int64_t key_stride,
-                               int n_keys, __nv_bfloat16* out, int ldo, int n_heads, int B, cudaStream_t st) {
+mw_status launch_cross_grouped(const mw_h* q, int ldq, const mw_h* k, const mw_h* v, int64_t key_stride,
+                               int n_keys, mw_h* out, int ldo, int n_heads, int B, cudaStream_t st) {
     const size_t smem = (size_t)G * n_keys * sizeof(float);
     static PerDeviceOnce attr_once;
     MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(cross_attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }));
@@ -985,7 +985,8 @@ __global__ void advance_forced_kernel(const int* __restrict__ forced, int per_ro
 __global__ void __launch_bounds__(SEL_THREADS)
 beam_candidates_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts, const uint8_t* __restrict__ sup,
                        const uint8_t* __restrict__ beg, const int* __restrict__ tokens, const int* __restrict__ gen_len,
-                       const int* __restrict__ last_ts, float* cand_val, int* cand_idx, float* row_lse, int max_new) {
+                       const int* __restrict__ last_ts, float* cand_val, int* cand_idx, float* row_lse, int max_new,
+                       DecCtl* ctl) {
     __shared__ ValIdx s_c[SEL_THREADS / 32];
     __shared__ ValIdx s_pick;
     const int r = blockIdx.x;
@@ -1044,6 +1045,9 @@ beam_candidates_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts
         __syncthreads();
     }
     if (tid == 0) row_lse[r] = lse;
+    // The step counters advance HERE: no CTA of this kernel reads them, and the kernel boundary orders the write before
+    // every CTA of beam_update_kernel (which used to advance them itself while its other CTAs were still reading pos).
+    if (blockIdx.x == 0 && tid == 0) { ctl->pos += 1; ctl->step += 1; }
 }
 
 // stage 2, one thread per chunk: merge the k rows' candidates, walk them in order, re-parent the beams
@@ -1057,7 +1061,7 @@ __global__ void beam_update_kernel(const GenOptsDev* __restrict__ opts, const fl
     const GenOptsDev o = *opts;
     const int k = o.beam, nc = 2 * k;
     const int b = blockIdx.x;
-    const int pos = ctl->pos;          // position fed this step; new token goes to pos+1
+    const int pos = ctl->pos - 1;      // position fed this step (beam_candidates_kernel already advanced the counter); new token goes to pos+1
     __shared__ float s_val[MAX_BEAM * NCAND];
     __shared__ int s_flat[MAX_BEAM * NCAND];
     __shared__ int s_parent[MAX_BEAM], s_tok[MAX_BEAM];
@@ -1154,7 +1158,6 @@ __global__ void beam_update_kernel(const GenOptsDev* __restrict__ opts, const fl
     }
     __syncthreads();
     if (tid == 0 && live > 0) gen_len[b] = gl + 1;
-    if (blockIdx.x == 0 && tid == 0) { ctl->pos += 1; ctl->step += 1; }
 }
 
 // after the last step: chunks still active contribute their live beams (best first) as hypotheses
@@ -1304,7 +1307,7 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
     const int d = c.d_model, ctx = c.n_text_ctx, T = c.n_audio_ctx;
     mw_status r;
     if (parts & PART_EMBED) {
-        embed_kernel<<<R, 128, 0, st>>>(s->cur_tok, (const __nv_bfloat16*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), s->ctl, s->x, d);
+        embed_kernel<<<R, 128, 0, st>>>(s->cur_tok, (const mw_h*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), s->ctl, s->x, d);
         MW_LAUNCH_CHECK();
     }
     const int* idx = beam > 1 ? s->self_idx[idx_phase] : nullptr;
@@ -1315,8 +1318,8 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
         if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st)) != MW_OK) return r;
         if (parts & PART_SELF) {
-            __nv_bfloat16* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
-            __nv_bfloat16* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
+            mw_h* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
+            mw_h* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
             dim3 grid(c.n_heads, R);
             decode_attn_kernel<true><<<grid, 128, ctx * sizeof(float), st>>>(
                 s->qkv, 3 * d, kc, vc, d, ctx, idx, ctx, s->ctl, 0, 1, s->qkv + d, s->qkv + 2 * d, 3 * d, s->att, d);
@@ -1326,7 +1329,7 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
         if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st)) != MW_OK) return r;
         if (parts & PART_CROSS) {
-            __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
+            mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             if (beam > 1) {
                 const int Bc = R / beam;
 #define MW_XG(g) case g: r = launch_cross_grouped<g>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d, c.n_heads, Bc, st); break
@@ -1370,7 +1373,7 @@ mw_status enqueue_select(mw_model* m, int B, int beam, int phase, cudaStream_t s
         return MW_OK;
     }
     beam_candidates_kernel<<<R, SEL_THREADS, 0, st>>>(s->logits, c.vocab, s->opts, s->sup_mask, s->begin_mask, s->tokens[phase],
-                                                      s->gen_len, s->last_ts[phase], s->cand_val, s->cand_idx, s->row_lse, s->max_new);
+                                                      s->gen_len, s->last_ts[phase], s->cand_val, s->cand_idx, s->row_lse, s->max_new, s->ctl);
     MW_LAUNCH_CHECK();
     beam_update_kernel<<<B, 128, 0, st>>>(s->opts, s->cand_val, s->cand_idx, s->row_lse, s->tokens[phase], s->tokens[phase ^ 1],
                                           s->gen_len, s->cum, s->last_ts[phase], s->last_ts[phase ^ 1], s->self_idx[phase],
@@ -1403,15 +1406,15 @@ mw_status capture_graph(DecoderState* s, cudaGraphExec_t* out, Fn&& enqueue) {
 // shared by the beams through the index table), pos = step = P-1 and the last prompt token as the next input.
 // Matters for the reference's own call, which passes an initial_prompt (/root/reference/transcribe.py:40,111).
 // ------------------------------------------------------------------------------------------------
-__global__ void embed_prefill_kernel(const int* __restrict__ prompt, const __nv_bfloat16* __restrict__ emb,
+__global__ void embed_prefill_kernel(const int* __restrict__ prompt, const mw_h* __restrict__ emb,
                                      const float* __restrict__ pos_emb, float* __restrict__ x, int Pm, int d) {
     const int r = blockIdx.x, p = r % Pm;
     const int tok = prompt[p];
     for (int i = threadIdx.x; i < d; i += blockDim.x)
-        x[(int64_t)r * d + i] = __bfloat162float(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)p * d + i];
+        x[(int64_t)r * d + i] = h2f(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)p * d + i];
 }
 
-__global__ void kv_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc,
+__global__ void kv_scatter_kernel(const mw_h* __restrict__ qkv, mw_h* __restrict__ kc, mw_h* __restrict__ vc,
                                   int Pm, int d, int ctx, int beam) {
     const int r = blockIdx.x, b = r / Pm, p = r - b * Pm;
     const uint4* src = reinterpret_cast<const uint4*>(qkv + (int64_t)r * 3 * d + d);
@@ -1438,7 +1441,7 @@ mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st)
     DecoderState* s = m->dec;
     const int d = c.d_model, ctx = c.n_text_ctx, T = c.n_audio_ctx, M = B * Pm, R = B * beam;
     mw_status r;
-    embed_prefill_kernel<<<M, 128, 0, st>>>(s->prompt, (const __nv_bfloat16*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), m->x, Pm, d);
+    embed_prefill_kernel<<<M, 128, 0, st>>>(s->prompt, (const mw_h*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), m->x, Pm, d);
     MW_LAUNCH_CHECK();
     auto gemm = [&](const void* A, int K, const void* W, const float* bias, const float* res, void* out, int N, bool gelu, bool f32) {
         GemmArgs a;
@@ -1449,8 +1452,8 @@ mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st)
     for (int l = 0; l < c.dec_layers; ++l) {
         auto W = [&](int id) { return m->dlw(l, id); };
         auto F = [&](int id) { return (const float*)m->dlw(l, id); };
-        __nv_bfloat16* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
-        __nv_bfloat16* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
+        mw_h* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
+        mw_h* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
         if ((r = layernorm_launch(m->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), m->ln, M, d, st)) != MW_OK) return r;
         if ((r = gemm(m->ln, d, W(MW_DL_WQKV), F(MW_DL_BQKV), nullptr, m->qkv, 3 * d, false, false)) != MW_OK) return r;
         kv_scatter_kernel<<<M, 128, 0, st>>>(m->qkv, kc, vc, Pm, d, ctx, beam);
@@ -1465,7 +1468,7 @@ mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st)
         if ((r = layernorm_launch(m->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), m->ln, M, d, st)) != MW_OK) return r;
         if ((r = gemm(m->ln, d, W(MW_DL_WXQ), F(MW_DL_BXQ), nullptr, m->att, d, false, false)) != MW_OK) return r;     // cross q
         {
-            __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
+            mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             if ((r = attention_launch_general(m->att, d, 0, kv, 2 * d, 0, d, m->ln, d, B, Pm, T, c.n_heads, st)) != MW_OK) return r;
         }
         if ((r = gemm(m->ln, d, W(MW_DL_WXO), F(MW_DL_BXO), m->x, m->x, d, false, true)) != MW_OK) return r;
@@ -1783,7 +1786,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
     MW_CUDA_CHECK(cudaEventCreate(&e1));
     auto one = [&](int l) -> mw_status {
         if (which == 0) {
-            __nv_bfloat16* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
+            mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             dim3 grid(c.n_heads, B);
             cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
             MW_LAUNCH_CHECK();

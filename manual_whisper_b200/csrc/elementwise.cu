@@ -14,7 +14,7 @@ template <int MAXV, int MODE = 0>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ out_v, int rows, int d) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_v);
+    mw_h* out = reinterpret_cast<mw_h*>(out_v);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -55,8 +55,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                 reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + (int64_t)row * d)[i * 32 + lane] = make_float4(y0, y1, y2, y3);
                 continue;
             }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(y2, y3);
+            mw_h2 h0 = f2h2(y0, y1);
+            mw_h2 h1 = f2h2(y2, y3);
             uint2 u;
             u.x = *reinterpret_cast<uint32_t*>(&h0);
             u.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -66,13 +66,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 
 // f32 [B, C, F] -> bf16 [B, F+2, C] with zero rows 0 and F+1
 __global__ void __launch_bounds__(256)
-features_to_time_major_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int F) {
+features_to_time_major_kernel(const float* __restrict__ in, mw_h* __restrict__ out, int C, int F) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const float* src = in + (int64_t)b * C * F;
-    __nv_bfloat16* dst = out + (int64_t)b * (F + 2) * C;
+    mw_h* dst = out + (int64_t)b * (F + 2) * C;
     for (int i = ty; i < 32; i += 8) {
         const int c = c0 + i, f = f0 + tx;
         tile[i][tx] = (c < C && f < F) ? src[(int64_t)c * F + f] : 0.0f;
@@ -80,13 +80,13 @@ features_to_time_major_kernel(const float* __restrict__ in, __nv_bfloat16* __res
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int f = f0 + i, c = c0 + tx;
-        if (f < F && c < C) dst[(int64_t)(f + 1) * C + c] = __float2bfloat16(tile[tx][i]);
+        if (f < F && c < C) dst[(int64_t)(f + 1) * C + c] = f2h(tile[tx][i]);
     }
     if (blockIdx.x == 0 && ty == 0) {
         const int c = c0 + tx;
         if (c < C) {
-            dst[c] = __float2bfloat16(0.0f);
-            dst[(int64_t)(F + 1) * C + c] = __float2bfloat16(0.0f);
+            dst[c] = f2h(0.0f);
+            dst[(int64_t)(F + 1) * C + c] = f2h(0.0f);
         }
     }
 }
@@ -135,7 +135,7 @@ mw_status layernorm_act_launch(const float* x, const float* gamma, const float* 
 
 mw_status features_to_time_major_launch(const float* in, void* out_bf16, int B, int C, int F, cudaStream_t st) {
     dim3 grid(ceil_div(F, 32), ceil_div(C, 32), B);
-    features_to_time_major_kernel<<<grid, 256, 0, st>>>(in, (__nv_bfloat16*)out_bf16, C, F);
+    features_to_time_major_kernel<<<grid, 256, 0, st>>>(in, (mw_h*)out_bf16, C, F);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

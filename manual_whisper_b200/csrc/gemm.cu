@@ -21,6 +21,11 @@ using namespace ptx;
 
 namespace {
 
+#ifdef MW_STORAGE_BF16
+constexpr CUtensorMapDataType MW_TMA_DTYPE = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+constexpr CUtensorMapDataType MW_TMA_DTYPE = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int NUM_EPI_WARPS = 8;
@@ -120,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc = make_idesc_h16(BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -135,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         // +32 bytes per 16-element K step inside the 128-byte swizzle row (address field is >>4)
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_h16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -215,13 +220,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
-                        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ld_out + n0);
+                        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<mw_h*>(p.out) + out_row * p.ld_out + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                            mw_h2 h0 = f2h2(v[8 * j], v[8 * j + 1]);
+                            mw_h2 h1 = f2h2(v[8 * j + 2], v[8 * j + 3]);
+                            mw_h2 h2 = f2h2(v[8 * j + 4], v[8 * j + 5]);
+                            mw_h2 h3 = f2h2(v[8 * j + 6], v[8 * j + 7]);
                             uint4 u;
                             u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                             u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -296,7 +301,7 @@ mw_status encode_tensor_map(CUtensorMap* map, const void* base, int rank, const 
     cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = fn(map, MW_TMA_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -344,7 +349,7 @@ mw_status gemm_launch(const GemmArgs& a, cudaStream_t st) {
 
 }  // namespace mw
 
-extern "C" mw_status mw_gemm_bf16(const void* d_a, const void* d_w, const float* d_bias, const float* d_residual,
+extern "C" mw_status mw_gemm_h16(const void* d_a, const void* d_w, const float* d_bias, const float* d_residual,
                                   void* d_out, int M, int N, int K, int gelu, int out_f32, void* stream) {
     mw::GemmArgs a;
     a.a = d_a; a.a_row_stride = K; a.a_batch_stride = (int64_t)M * K;

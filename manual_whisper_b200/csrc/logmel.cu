@@ -115,7 +115,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
 // grid: (ceil(n_frames/32), n_chunks); block 256 (8 warps, warp w handles mels w, w+8, ...)
 __global__ void __launch_bounds__(256)
 logmel_finalize_kernel(float* __restrict__ out, const unsigned* __restrict__ gmax, int n_mels, int64_t n_frames,
-                       __nv_bfloat16* __restrict__ out_t /* [chunks, n_frames+2, n_mels] or null */) {
+                       mw_h* __restrict__ out_t /* [chunks, n_frames+2, n_mels] or null */) {
     __shared__ float tile[128][33];
     const int chunk = blockIdx.y;
     const int64_t f0 = (int64_t)blockIdx.x * 32;
@@ -134,21 +134,21 @@ logmel_finalize_kernel(float* __restrict__ out, const unsigned* __restrict__ gma
         }
         if (out_t) {
             __syncthreads();
-            __nv_bfloat16* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
+            mw_h* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
             const int mcount = min(128, n_mels - m0);
             // 32 frames x mcount mels, mel fastest
             for (int i = threadIdx.x; i < 32 * mcount; i += 256) {
                 const int f = i / mcount, m = i - f * mcount;
-                if (f0 + f < n_frames) ot[(f0 + f + 1) * n_mels + m0 + m] = __float2bfloat16(tile[m][f]);
+                if (f0 + f < n_frames) ot[(f0 + f + 1) * n_mels + m0 + m] = f2h(tile[m][f]);
             }
             __syncthreads();
         }
     }
     if (out_t && blockIdx.x == 0) {
-        __nv_bfloat16* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
+        mw_h* ot = out_t + (int64_t)chunk * (n_frames + 2) * n_mels;
         for (int i = threadIdx.x; i < n_mels; i += 256) {
-            ot[i] = __float2bfloat16(0.0f);
-            ot[(n_frames + 1) * n_mels + i] = __float2bfloat16(0.0f);
+            ot[i] = f2h(0.0f);
+            ot[(n_frames + 1) * n_mels + i] = f2h(0.0f);
         }
     }
 }
@@ -248,7 +248,7 @@ static mw_status run_logmel(mw_logmel_plan* p, const float* d_audio, int64_t n_a
                                                                 n_frames, p->n_mels, n_chunks, p->d_tables, p->d_lo, p->d_cnt,
                                                                 p->d_off, p->d_w, p->nnz, d_out, p->d_gmax);
     MW_LAUNCH_CHECK();
-    logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (__nv_bfloat16*)d_out_t);
+    logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (mw_h*)d_out_t);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

@@ -20,7 +20,7 @@ mw_status model_alloc(mw_model* m, void** ptr, int64_t bytes, bool zero) {
     return MW_OK;
 }
 
-static mw_status encode_from_time_major(mw_model* m, const __nv_bfloat16* mel_t, int B, void* d_enc_out, cudaStream_t st) {
+static mw_status encode_from_time_major(mw_model* m, const mw_h* mel_t, int B, void* d_enc_out, cudaStream_t st) {
     const mw_model_config& c = m->cfg;
     const int T = c.n_audio_ctx, F = 2 * T, d = c.d_model;
     mw_status s;
@@ -129,7 +129,7 @@ extern "C" mw_status mw_encode_t(mw_model* m, const void* d_mel_t, int B, void* 
     MW_REQUIRE(m && d_mel_t && d_enc_out, "mw_encode_t: null argument");
     MW_REQUIRE(B > 0 && B <= m->cfg.max_batch, "mw_encode_t: B=%d outside 1..max_batch=%d", B, m->cfg.max_batch);
     mw::DeviceGuard guard(m->cfg.device);
-    return mw::encode_from_time_major(m, (const __nv_bfloat16*)d_mel_t, B, d_enc_out, (cudaStream_t)stream);
+    return mw::encode_from_time_major(m, (const mw_h*)d_mel_t, B, d_enc_out, (cudaStream_t)stream);
 }
 
 extern "C" mw_status mw_encode(mw_model* m, const float* d_mel, int B, void* d_enc_out, void* stream) {

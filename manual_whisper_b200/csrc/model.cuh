@@ -11,13 +11,13 @@ struct mw_model {
     std::vector<void*> allocations;
 
     // ---- encoder workspace (max_batch chunks)
-    __nv_bfloat16* mel_t = nullptr;      // [B, F+2, n_mels]   F = 2*n_audio_ctx
-    __nv_bfloat16* h1 = nullptr;         // [B, F+2, d]        conv1 output, rows 0 and F+1 stay zero
+    mw_h* mel_t = nullptr;      // [B, F+2, n_mels]   F = 2*n_audio_ctx
+    mw_h* h1 = nullptr;         // [B, F+2, d]        conv1 output, rows 0 and F+1 stay zero
     float* x = nullptr;                  // [B*T, d]           fp32 residual stream
-    __nv_bfloat16* ln = nullptr;         // [B*T, d]
-    __nv_bfloat16* qkv = nullptr;        // [B*T, 3d]
-    __nv_bfloat16* att = nullptr;        // [B*T, d]
-    __nv_bfloat16* mlp = nullptr;        // [B*T, ffn]
+    mw_h* ln = nullptr;         // [B*T, d]
+    mw_h* qkv = nullptr;        // [B*T, 3d]
+    mw_h* att = nullptr;        // [B*T, d]
+    mw_h* mlp = nullptr;        // [B*T, ffn]
 
     // ---- decoder state (decoder.cu)
     struct DecoderState* dec = nullptr;

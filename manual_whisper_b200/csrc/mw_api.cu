@@ -17,3 +17,10 @@ void set_error(const char* fmt, ...) {
 extern "C" int mw_abi_version(void) { return MW_ABI_VERSION; }
 extern "C" const char* mw_last_error(void) { return mw::g_err; }
 extern "C" uint64_t mw_launch_count(void) { return mw::g_launches.load(); }
+extern "C" int mw_storage_dtype(void) {
+#ifdef MW_STORAGE_BF16
+    return 1;
+#else
+    return 0;
+#endif
+}

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -9,6 +10,36 @@
 #include <mutex>
 
 #include "../../include/mw_b200.h"
+
+// ---- 16-bit storage type of activations, K/V caches and weight matrices.
+// Default fp16: it is the reference's own GPU compute type (compute_type="float16", /root/reference/transcribe_colab.ipynb:119),
+// Whisper checkpoints are published in fp16 (so weights are exact), and its 11-bit significand puts the engine's logit noise
+// 8x below bf16's - which is what lets greedy ids match the fp32 oracle.  Accumulation, the residual
+// stream, softmax statistics and logits are fp32 either way.  -DMW_STORAGE_BF16 builds the bf16 variant for A/B runs.
+#ifdef MW_STORAGE_BF16
+typedef __nv_bfloat16 mw_h;
+typedef __nv_bfloat162 mw_h2;
+#define MW_STORAGE_NAME "bf16"
+#define MW_MMA_SYNC_TYPE "bf16"
+#define MW_UMMA_FMT 1u
+__device__ __forceinline__ mw_h f2h(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float h2f(mw_h v) { return __bfloat162float(v); }
+__device__ __forceinline__ mw_h2 f2h2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ float2 h22f2(mw_h2 v) { return __bfloat1622float2(v); }
+#else
+typedef __half mw_h;
+typedef __half2 mw_h2;
+#define MW_STORAGE_NAME "fp16"
+#define MW_MMA_SYNC_TYPE "f16"
+#define MW_UMMA_FMT 0u
+// saturating: a value beyond the fp16 range becomes +-65504, never inf (which would turn into NaN downstream)
+__device__ __forceinline__ mw_h f2h(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
+__device__ __forceinline__ float h2f(mw_h v) { return __half2float(v); }
+__device__ __forceinline__ mw_h2 f2h2(float a, float b) {
+    return __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+}
+__device__ __forceinline__ float2 h22f2(mw_h2 v) { return __half22float2(v); }
+#endif
 
 namespace mw {
 

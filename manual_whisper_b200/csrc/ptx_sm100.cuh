@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "mw_common.cuh"
 
 namespace mw {
 namespace ptx {
@@ -86,8 +87,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate.  One thread issues.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]^T, 16-bit inputs (mw_h), fp32 accumulate.  One thread issues.
+__device__ __forceinline__ void umma_h16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -132,11 +133,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
     return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32.
-//   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
+// Instruction descriptor for kind::f16: 16-bit x 16-bit -> fp32 (MW_UMMA_FMT: 0 = fp16, 1 = bf16, mw_common.cuh).
+//   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format
 //   [15] A major (0 = K)  [16] B major (0 = K, 1 = MN)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_major = 0) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc_h16(int M, int N, int b_mn_major = 0) {
+    return (1u << 4) | (MW_UMMA_FMT << 7) | (MW_UMMA_FMT << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 

@@ -27,16 +27,16 @@ struct mw_w2v {
     std::vector<void*> allocations;
     int vocab_pad = 0;
     int T_max[7] = {};                    // frames after each conv layer at max_samples
-    __nv_bfloat16* act_a = nullptr;       // [B, T_0, C]  conv0 / even layers' output
-    __nv_bfloat16* act_b = nullptr;       // [B, T_1, C]  odd layers' output
+    mw_h* act_a = nullptr;       // [B, T_0, C]  conv0 / even layers' output
+    mw_h* act_b = nullptr;       // [B, T_1, C]  odd layers' output
     float* conv_f32 = nullptr;            // [B, T_1, C]  GEMM output ahead of LayerNorm
     float* feat = nullptr;                // [B*T, C]     last conv layer after LN + GELU (fp32: feeds a LayerNorm)
     float* x = nullptr;                   // [B*T, d]     fp32 residual stream
-    __nv_bfloat16* xg = nullptr;          // [B, G, T + pos_kernel, 64] group-major, zero padded
-    __nv_bfloat16* ln = nullptr;          // [B*T, max(d, C)]
-    __nv_bfloat16* qkv = nullptr;         // [B*T, 3d]
-    __nv_bfloat16* att = nullptr;         // [B*T, d]
-    __nv_bfloat16* mlp = nullptr;         // [B*T, ffn]
+    mw_h* xg = nullptr;          // [B, G, T + pos_kernel, 64] group-major, zero padded
+    mw_h* ln = nullptr;          // [B*T, max(d, C)]
+    mw_h* qkv = nullptr;         // [B*T, 3d]
+    mw_h* att = nullptr;         // [B*T, d]
+    mw_h* mlp = nullptr;         // [B*T, ffn]
     float* logits = nullptr;              // [B*T, vocab_pad]
     int* d_frames = nullptr;              // [B] valid frames per window of the current call
 
@@ -69,7 +69,7 @@ template <int NP>
 __global__ void __launch_bounds__(256)
 w2v_conv0_kernel(const float* __restrict__ audio, int64_t n_audio, const int64_t* __restrict__ offs, const int* __restrict__ lens,
                  const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int T0) {
+                 const float* __restrict__ beta, mw_h* __restrict__ out, int T0) {
     constexpr int C = 64 * NP;
     __shared__ float sw[10][C];
     __shared__ float sb[C], sg[C], sbe[C];
@@ -118,20 +118,20 @@ w2v_conv0_kernel(const float* __restrict__ audio, int64_t n_audio, const int64_t
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         const float rstd = rsqrtf(q / (float)C + 1e-5f);
-        __nv_bfloat16* o = out + ((int64_t)b * T0 + t) * C;
+        mw_h* o = out + ((int64_t)b * T0 + t) * C;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const int c = 2 * lane + 64 * p;
             const float y0 = gelu_exact((v[p][0] - mean) * rstd * sg[c] + sbe[c]);
             const float y1 = gelu_exact((v[p][1] - mean) * rstd * sg[c + 1] + sbe[c + 1]);
-            *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(y0, y1);
+            *reinterpret_cast<mw_h2*>(o + c) = f2h2(y0, y1);
         }
     }
 }
 
 // x f32 [n, T, d] -> bf16 [n, G, T + kp, 64]: row t' holds frame t' - kp/2, zero outside the window's valid frames
 __global__ void __launch_bounds__(256)
-w2v_group_major_kernel(const float* __restrict__ x, const int* __restrict__ frames, __nv_bfloat16* __restrict__ xg, int T, int d,
+w2v_group_major_kernel(const float* __restrict__ x, const int* __restrict__ frames, mw_h* __restrict__ xg, int T, int d,
                        int kp) {
     const int tp = blockIdx.x, b = blockIdx.y;
     const int t = tp - kp / 2;
@@ -140,7 +140,7 @@ w2v_group_major_kernel(const float* __restrict__ x, const int* __restrict__ fram
     const float* src = x + ((int64_t)b * T + t) * d;
     for (int c = threadIdx.x; c < d; c += 256) {
         const int g = c >> 6, ci = c & 63;
-        xg[(((int64_t)b * G + g) * (T + kp) + tp) * 64 + ci] = __float2bfloat16(valid ? src[c] : 0.0f);
+        xg[(((int64_t)b * G + g) * (T + kp) + tp) * 64 + ci] = f2h(valid ? src[c] : 0.0f);
     }
 }
 
@@ -355,7 +355,7 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
         else w2v_conv0_kernel<2><<<grid, 256, 0, st>>>(d_audio, n_audio, d_offsets, d_lengths, w0, b0, g0, be0, m->act_a, Tl[0]);
         MW_LAUNCH_CHECK();
     }
-    const __nv_bfloat16* in = m->act_a;
+    const mw_h* in = m->act_a;
     for (int l = 1; l < 7; ++l) {
         GemmArgs a;
         a.a = in; a.a_row_stride = (int64_t)CONV_S[l] * C; a.a_batch_stride = (int64_t)Tl[l - 1] * C;
@@ -368,7 +368,7 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
         if ((s = layernorm_act_launch(m->conv_f32, (const float*)m->gw(MW_A_CONV0_W + 4 * l + 2),
                                       (const float*)m->gw(MW_A_CONV0_W + 4 * l + 3), out, n * Tl[l], C, l == 6 ? 2 : 1, st)) != MW_OK)
             return s;
-        in = (const __nv_bfloat16*)out;
+        in = (const mw_h*)out;
     }
     const int rows = n * T;
     if ((s = layernorm_launch(m->feat, (const float*)m->gw(MW_A_FP_LN_G), (const float*)m->gw(MW_A_FP_LN_B), m->ln, rows, C, st)) != MW_OK) return s;
@@ -386,7 +386,7 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
         for (int g = 0; g < G; ++g) {
             GemmArgs a;
             a.a = m->xg + (int64_t)g * (T + kp) * 64; a.a_row_stride = 64; a.a_batch_stride = (int64_t)G * (T + kp) * 64;
-            a.w = (const __nv_bfloat16*)m->gw(MW_A_POS_W) + (int64_t)g * 64 * kp * 64; a.w_row_stride = (int64_t)kp * 64;
+            a.w = (const mw_h*)m->gw(MW_A_POS_W) + (int64_t)g * 64 * kp * 64; a.w_row_stride = (int64_t)kp * 64;
             a.bias = (const float*)m->gw(MW_A_POS_B) + g * 64;
             a.residual = m->x + g * 64; a.res_batch_rows = T; a.ld_res = d;
             a.out = m->x + g * 64; a.out_batch_rows = T; a.ld_out = d;

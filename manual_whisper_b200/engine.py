@@ -25,11 +25,13 @@ _DEC = ["ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "lnx_g", "lnx_b", "wxq", "
 
 
 def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, device: torch.device) -> List[torch.Tensor]:
-    """HF-named state dict -> the engine's weight table (bf16 matrices, fp32 vectors, engine layouts)."""
+    """HF-named state dict -> the engine's weight table (16-bit matrices in the library's storage type - fp16 unless built
+    otherwise, include/mw_b200.h: mw_storage_dtype - fp32 vectors, engine layouts)."""
     d = dims.d_model
+    h16 = _lib.storage_dtype()
 
     def mat(t):
-        return t.to(device=device, dtype=torch.bfloat16).contiguous()
+        return t.to(device=device, dtype=h16).contiguous()
 
     def vec(t):
         return t.to(device=device, dtype=torch.float32).contiguous()
@@ -92,6 +94,7 @@ class Engine:
         """`packed` = the weight table of another Engine on the same device (weights are borrowed pointers, so
         several engines — each with its own workspace — can share one copy)."""
         self.lib = _lib.load()
+        self.h16 = _lib.storage_dtype()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if dev.type != "cuda":
             raise ValueError("unsupported device %s: the B200 engine runs on CUDA devices only (no CPU fallback)" % device)
@@ -131,20 +134,20 @@ class Engine:
 
     # ---- S2
     def encode(self, features: torch.Tensor) -> torch.Tensor:
-        """features f32 [B, n_mels, 2*n_audio_ctx] (CUDA) -> bf16 [B, n_audio_ctx, d]."""
+        """features f32 [B, n_mels, 2*n_audio_ctx] (CUDA) -> h16 [B, n_audio_ctx, d]."""
         assert features.is_cuda and features.dtype == torch.float32 and features.is_contiguous()
         B = features.shape[0]
         assert features.shape[1:] == (self.dims.n_mels, 2 * self.dims.n_audio_ctx), features.shape
-        out = torch.empty((B, self.dims.n_audio_ctx, self.dims.d_model), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((B, self.dims.n_audio_ctx, self.dims.d_model), dtype=self.h16, device=self.device)
         _lib.check(self.lib.mw_encode(self.handle, features.data_ptr(), B, out.data_ptr(), self._stream()), "mw_encode")
         return out
 
     def encode_time_major(self, features_t: torch.Tensor) -> torch.Tensor:
-        """features bf16 [B, 2*n_audio_ctx + 2, n_mels] as emitted by mw_logmel (zero edge rows)."""
-        assert features_t.is_cuda and features_t.dtype == torch.bfloat16 and features_t.is_contiguous()
+        """features h16 [B, 2*n_audio_ctx + 2, n_mels] as emitted by mw_logmel (zero edge rows)."""
+        assert features_t.is_cuda and features_t.dtype == self.h16 and features_t.is_contiguous()
         B = features_t.shape[0]
         assert features_t.shape[1:] == (2 * self.dims.n_audio_ctx + 2, self.dims.n_mels), features_t.shape
-        out = torch.empty((B, self.dims.n_audio_ctx, self.dims.d_model), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((B, self.dims.n_audio_ctx, self.dims.d_model), dtype=self.h16, device=self.device)
         _lib.check(self.lib.mw_encode_t(self.handle, features_t.data_ptr(), B, out.data_ptr(), self._stream()),
                    "mw_encode_t")
         return out
@@ -155,7 +158,7 @@ class Engine:
                  suppress_blank: bool = True, suppress_tokens: Optional[Sequence[int]] = (-1,),
                  max_initial_timestamp_index: int = 50, num_hypotheses: int = 1,
                  forced_eot_len: int = 0) -> List[GenerationResult]:
-        assert enc.is_cuda and enc.dtype == torch.bfloat16 and enc.is_contiguous()
+        assert enc.is_cuda and enc.dtype == self.h16 and enc.is_contiguous()
         B = enc.shape[0]
         prompt = [int(t) for t in prompt]
         if not prompt:
@@ -193,7 +196,7 @@ class Engine:
 
     def decoder_logits(self, enc: torch.Tensor, tokens_in: np.ndarray) -> torch.Tensor:
         """Teacher-forced logits f32 [B, n, vocab] for tokens_in int32 [B, n] (parity tests)."""
-        assert enc.is_cuda and enc.dtype == torch.bfloat16 and enc.is_contiguous()
+        assert enc.is_cuda and enc.dtype == self.h16 and enc.is_contiguous()
         tk = np.ascontiguousarray(tokens_in, dtype=np.int32)
         B, n = tk.shape
         out = torch.empty((B, n, self.dims.vocab), dtype=torch.float32, device=self.device)

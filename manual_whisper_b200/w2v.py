@@ -55,12 +55,13 @@ def effective_pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 
 def random_init_w2v(dims: W2vDims, seed: int = 0, std: float = 0.05) -> Dict[str, torch.Tensor]:
-    """Seeded random-init weights with the Hugging Face ``Wav2Vec2ForCTC`` key names; every matrix is bf16-representable so
+    """Seeded random-init weights with the Hugging Face ``Wav2Vec2ForCTC`` key names; every matrix is representable in the engine's 16-bit storage (weights.round_shared) so
     the CUDA engine and this oracle hold identical values.  The positional conv is stored as its effective weight."""
     g = torch.Generator().manual_seed(seed)
 
     def rnd(*shape, s=std):
-        return (torch.randn(*shape, generator=g) * s).to(torch.bfloat16).to(torch.float32)
+        from .weights import round_shared
+        return round_shared(torch.randn(*shape, generator=g) * s)
 
     sd: Dict[str, torch.Tensor] = {}
     c_in = 1

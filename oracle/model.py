@@ -9,8 +9,9 @@ this container, so this follows SURVEY.md Appendix A.7-A.8 and is pinned against
 in-container implementation transformers/models/whisper/modeling_whisper.py on the same weights
 (tests/test_oracle_model.py).  PARITY PINNED BY: HF twin; the reference itself pins nothing.
 
-``emulate_bf16=True`` rounds activations to bf16 at exactly the points where the CUDA engine stores
-bf16 (DESIGN.md "rounding points"), keeping fp32 accumulation; weights are bf16-representable on both
+``emulate=True`` rounds activations at exactly the points where the CUDA engine stores 16-bit values
+(DESIGN.md "rounding points") - to fp16, the engine's storage type (or bf16 when MW_STORAGE_BF16=1 selects the A/B
+build; "fp16" / "bf16" force one) - keeping fp32 accumulation; weights are exactly representable on both
 sides already.  With it off this is the plain fp32 ground truth.
 """
 from __future__ import annotations
@@ -22,15 +23,25 @@ import torch
 import torch.nn.functional as F
 
 
-def _r(x: torch.Tensor, on: bool) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32) if on else x
+def engine_rounding() -> str:
+    """Storage type of the library build under test: fp16 unless MW_STORAGE_BF16=1 built the bf16 variant."""
+    import os
+    return "bf16" if os.environ.get("MW_STORAGE_BF16") == "1" else "fp16"
+
+
+def _r(x: torch.Tensor, on) -> torch.Tensor:
+    """Round to the engine's storage type at a rounding point.  `on` is False (fp32 ground truth), True / "bf16"
+    (what the engine stores) or "fp16" (analysis only: what an fp16-storing engine would do, scripts/parity_probe.py)."""
+    if not on:
+        return x
+    return x.to(torch.float16 if on == "fp16" else torch.bfloat16).to(torch.float32)
 
 
 class OracleWhisper:
-    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate_bf16: bool = False):
+    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate=False):
         self.dims = dims
         self.sd = {k: v.to(torch.float32) for k, v in sd.items()}
-        self.emu = emulate_bf16
+        self.emu = engine_rounding() if emulate is True else emulate
         self.scale = dims.d_head ** -0.5
 
     # ------------------------------------------------------------------ helpers
@@ -53,7 +64,7 @@ class OracleWhisper:
         if round_p:
             # the encoder's flash kernel rounds the un-normalised exp() to bf16 before P.V
             m = s.max(dim=-1, keepdim=True).values
-            e = _r(torch.exp(s - m), True)
+            e = _r(torch.exp(s - m), round_p)
             o = torch.matmul(e, v) / torch.exp(s - m).sum(dim=-1, keepdim=True)
         else:
             o = torch.matmul(p, v)

@@ -11,7 +11,8 @@ processor normalisation) and takes ``log_softmax(model(x).logits)``.  The checkp
 weights are random-init of that architecture (HF key names).  PARITY PINNED BY: transformers'
 modeling_wav2vec2.py, importable here, on the same weights (tests/test_oracle_align.py).
 
-``emulate_bf16=True`` rounds activations where the CUDA engine stores bf16 (GEMM operands), keeping fp32 accumulation.
+``emulate=True`` rounds activations where the CUDA engine stores 16-bit values (GEMM operands; fp16, or bf16 for the
+MW_STORAGE_BF16=1 build - oracle/model.py: engine_rounding), keeping fp32 accumulation.
 """
 from __future__ import annotations
 
@@ -21,8 +22,7 @@ import torch
 import torch.nn.functional as F
 
 
-def _r(x: torch.Tensor, on: bool) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32) if on else x
+from .model import _r, engine_rounding
 
 
 def pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -40,13 +40,13 @@ def pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
 class OracleWav2Vec2:
     """logits = lm_head(encoder(feature_projection(conv_stack(waveform)))), one waveform at a time like whisperx.align."""
 
-    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate_bf16: bool = False):
+    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate=False):
         self.dims = dims
         self.sd = {k: v.to(torch.float32) for k, v in sd.items()}
-        self.emu = emulate_bf16
+        self.emu = engine_rounding() if emulate is True else emulate
         self.w_pos = pos_conv_weight(self.sd)
-        if emulate_bf16:
-            self.w_pos = _r(self.w_pos, True)
+        if self.emu:
+            self.w_pos = _r(self.w_pos, self.emu)
 
     def _ln(self, x, prefix, eps=1e-5):
         return F.layer_norm(x, (x.shape[-1],), self.sd[prefix + ".weight"], self.sd[prefix + ".bias"], eps)
@@ -97,7 +97,7 @@ class OracleWav2Vec2:
             if self.emu:   # the flash kernel rounds the un-normalised exp() to bf16 before P.V, sums unrounded
                 m = s.max(dim=-1, keepdim=True).values
                 e = torch.exp(s - m)
-                o = torch.matmul(_r(e, True), v) / e.sum(dim=-1, keepdim=True)
+                o = torch.matmul(_r(e, self.emu), v) / e.sum(dim=-1, keepdim=True)
             else:
                 o = torch.matmul(torch.softmax(s, dim=-1), v)
             o = o.transpose(0, 1).reshape(T, d.d_model)

@@ -5,10 +5,10 @@ lib = _lib.load(); dev = torch.device("cuda:0")
 B, T, H = 32, 1500, 20; d = H * 64
 qkv = torch.randn(B * T, 3 * d, device=dev).bfloat16(); out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-for _ in range(3): lib.mw_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, T, H, st)
+for _ in range(3): lib.mw_attention_h16(qkv.data_ptr(), out.data_ptr(), B, T, H, st)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10): lib.mw_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, T, H, st)
+for _ in range(10): lib.mw_attention_h16(qkv.data_ptr(), out.data_ptr(), B, T, H, st)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 fl = 4.0 * T * T * d * B

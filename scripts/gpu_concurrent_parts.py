@@ -9,7 +9,7 @@ from bench import device_weights, MODEL, BATCH
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 dev = torch.device("cuda:0"); dims = model_dims(MODEL)
-pipe = mw.load_model(MODEL, "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1},
+pipe = mw.load_model(MODEL, "cuda", compute_type="float16", language="zh", asr_options={"beam_size": 1},
                      vad_model=mw.InjectedVad([]), model=device_weights(dims, dev, seed=1234), max_batch=BATCH, streams_per_device=S)
 GB = {"gemm": 14 * dims.d_model ** 2 * 2 * dims.dec_layers / 1e9, "cross": BATCH * 1500 * 2 * dims.d_model * 2 * dims.dec_layers / 1e9,
       "ln": 3 * BATCH * dims.d_model * 6 * dims.dec_layers / 1e9, "layers+logits": None}

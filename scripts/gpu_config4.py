@@ -12,7 +12,7 @@ wins = mw.merge_chunks(turns, 30)
 for name in ("small", "medium"):
     dims = model_dims(name); tok = special_tokens(dims.vocab)
     sd = random_init(dims, seed=1234, scheme="lively")
-    pipe = mw.load_model(name, "cuda", compute_type="bfloat16", language="en", model=sd, max_batch=16, streams_per_device=2,
+    pipe = mw.load_model(name, "cuda", compute_type="float16", language="en", model=sd, max_batch=16, streams_per_device=2,
                          asr_options={"beam_size": 5, "patience": 1, "length_penalty": 1, "without_timestamps": False},
                          vad_model=mw.InjectedVad(turns))
     pipe.transcribe(audio[: 16000 * 120], batch_size=16)
@@ -28,7 +28,7 @@ for name in ("small", "medium"):
         from oracle.generate import generate, GenOptions
         n = 3
         offs = [int(w["start"] * 16000) for w in wins[:n]]; lens = [int(w["end"] * 16000) - o for w, o in zip(wins[:n], offs)]
-        emu = OracleWhisper(dims, sd, emulate_bf16=True)
+        emu = OracleWhisper(dims, sd, emulate=True)
         with torch.no_grad():
             ref = generate(emu, emu.encode(log_mel_chunks(audio, offs, lens, 80)), [tok.sot, tok.lang_id("en"), tok.transcribe], tok,
                            GenOptions(beam_size=5))

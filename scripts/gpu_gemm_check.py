@@ -14,7 +14,7 @@ def run(M, N, K, bias=False, gelu=False, resid=False, out_f32=False):
     r = torch.randn(M, N, device=dev) if resid else None
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.mw_gemm_bf16(a.data_ptr(), w.data_ptr(), b.data_ptr() if bias else None, r.data_ptr() if resid else None,
+    _lib.check(lib.mw_gemm_h16(a.data_ptr(), w.data_ptr(), b.data_ptr() if bias else None, r.data_ptr() if resid else None,
                                 out.data_ptr(), M, N, K, int(gelu), int(out_f32), st), "gemm")
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
@@ -34,10 +34,10 @@ def bench(M, N, K, gelu=False, iters=20):
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev); out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for _ in range(3): lib.mw_gemm_bf16(a.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0, st)
+    for _ in range(3): lib.mw_gemm_h16(a.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): lib.mw_gemm_bf16(a.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0, st)
+    for _ in range(iters): lib.mw_gemm_h16(a.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     e0.record()

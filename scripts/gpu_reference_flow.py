@@ -19,7 +19,7 @@ path = os.path.join(tempfile.mkdtemp(), "meeting.wav")
 with wave.open(path, "wb") as w:
     w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000); w.writeframes(pcm.tobytes())
 del up, pcm
-pipe = mw.load_model(MODEL, "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1},
+pipe = mw.load_model(MODEL, "cuda", compute_type="float16", language="zh", asr_options={"beam_size": 1},
                      vad_model=mw.InjectedVad(turns), model=device_weights(model_dims(MODEL), dev, seed=1234), max_batch=BATCH,
                      streams_per_device=8)
 model_a, meta = mw.load_align_model("zh", "cuda", max_batch=16)

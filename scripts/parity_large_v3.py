@@ -26,7 +26,7 @@ t0 = time.time(); sd = random_init(dims, seed=1234, scheme=scheme); t_init = tim
 audio, turns = mw.synthetic_speech(N * 30.0 + 5, seed=1)
 wins = mw.merge_chunks(turns, 30)[:N]
 offs = [int(w["start"] * 16000) for w in wins]; lens = [int(w["end"] * 16000) - o for w, o in zip(wins, offs)]
-pipe = mw.load_model(MODEL, "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1}, model=sd,
+pipe = mw.load_model(MODEL, "cuda", compute_type="float16", language="zh", asr_options={"beam_size": 1}, model=sd,
                      vad_model=mw.InjectedVad([(w["start"], w["end"]) for w in wins]), max_batch=max(N, 1), streams_per_device=1)
 model = pipe.model
 model.max_length = MAXLEN
@@ -41,7 +41,7 @@ out = {"model": MODEL, "windows": N, "max_length": MAXLEN, "init_scheme": scheme
 prompt = [tok.sot, tok.lang_id("zh"), tok.transcribe, tok.no_timestamps]
 torch.set_num_threads(os.cpu_count() or 8)
 for name, emu in (("fp32", False), ("bf16_rounding", True)):
-    orc = OracleWhisper(dims, sd, emulate_bf16=emu)
+    orc = OracleWhisper(dims, sd, emulate=emu)
     t0 = time.time()
     with torch.no_grad():
         enc = orc.encode(mel)

@@ -10,7 +10,7 @@ dev = torch.device("cuda:0"); dims = model_dims(MODEL)
 sd = device_weights(dims, dev, seed=1234)
 audio_np, turns = mw.synthetic_speech(HOUR_S, seed=1)
 pinned = torch.empty(len(audio_np), dtype=torch.float32, pin_memory=True); pinned.numpy()[:] = audio_np
-pipe = mw.load_model(MODEL, "cuda", compute_type="bfloat16", language="zh", asr_options={"beam_size": 1},
+pipe = mw.load_model(MODEL, "cuda", compute_type="float16", language="zh", asr_options={"beam_size": 1},
                      vad_model=mw.InjectedVad(turns), model=sd, max_batch=BATCH, streams_per_device=streams)
 for _ in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()

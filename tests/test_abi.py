@@ -33,7 +33,8 @@ def test_ctypes_signatures_cover_header(built_lib):
     from manual_whisper_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()
     lib = _lib.load()
-    assert lib.mw_abi_version() == 1
+    assert lib.mw_abi_version() == 2
+    assert lib.mw_storage_dtype() in (0, 1)
     assert isinstance(lib.mw_launch_count(), int)
 
 

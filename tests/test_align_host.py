@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from manual_whisper_b200 import _lib
+
 from manual_whisper_b200 import alignment as AL
 from manual_whisper_b200.w2v import W2vDims, random_init_w2v, effective_pos_conv_weight
 
@@ -67,7 +69,7 @@ def test_pack_w2v_weights_layouts():
     assert len(packed) == 38 + 12
     assert packed[0].shape == (128, 10) and packed[0].dtype == torch.float32
     w1 = sd["wav2vec2.feature_extractor.conv_layers.1.conv.weight"]
-    assert packed[4].shape == (128, 3 * 128) and packed[4].dtype == torch.bfloat16
+    assert packed[4].shape == (128, 3 * 128) and packed[4].dtype == _lib.storage_dtype()
     assert torch.equal(packed[4].float()[5, 2 * 128 + 7], w1[5, 7, 2])            # [co][tap][ci]
     wp = effective_pos_conv_weight(sd)                                          # [d, 64, taps]
     assert packed[32].shape == (2, 64, 4, 64)

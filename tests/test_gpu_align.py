@@ -31,7 +31,7 @@ def _oracle_emissions(dims, sd, wave, emulate):
         w = torch.from_numpy(wave)
         if len(w) < 400:
             w = torch.nn.functional.pad(w, (0, 400 - len(w)))
-        return OracleWav2Vec2(dims, sd, emulate_bf16=emulate).emissions(w)
+        return OracleWav2Vec2(dims, sd, emulate=emulate).emissions(w)
 
 
 def test_emissions_match_oracle_on_ragged_batch(small):

@@ -63,7 +63,7 @@ def test_transcribe_accepts_device_resident_audio():
     from manual_whisper_b200.weights import random_init
     dims = custom_dims("pipe-small", 80, 128, 2, 2, 2, 512, 2048, n_audio_ctx=1500, n_text_ctx=16)
     audio, turns = mw.synthetic_speech(40.0, seed=4)
-    pipe = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+    pipe = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1},
                          vad_model=mw.InjectedVad(turns), model=random_init(dims, seed=5, scheme="lively"), dims=dims,
                          tokens=scaled_tokens(2048), max_batch=4)
     a = pipe.transcribe(audio, batch_size=4)

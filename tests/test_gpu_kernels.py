@@ -7,6 +7,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _h16():
+    from manual_whisper_b200 import _lib
+    return _lib.storage_dtype()
+
+
 @pytest.fixture(scope="module")
 def lib():
     from manual_whisper_b200 import _lib
@@ -24,13 +29,13 @@ def test_gemm(lib, M, N, K, mode):
     from manual_whisper_b200 import _lib
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(M * 7 + N)
-    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
-    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).to(_h16())
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).to(_h16())
     bias = torch.randn(N, device=dev, generator=g) if mode != "plain" else None
     res = torch.randn(M, N, device=dev, generator=g) if mode == "bias_resid_f32" else None
     f32 = mode == "bias_resid_f32"
-    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    _lib.check(lib.mw_gemm_bf16(a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else _h16())
+    _lib.check(lib.mw_gemm_h16(a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                 res.data_ptr() if res is not None else None, out.data_ptr(), M, N, K,
                                 int(mode == "bias_gelu"), int(f32), _stream()), "gemm")
     ref = a.float() @ w.float().t()
@@ -46,8 +51,8 @@ def test_gemm(lib, M, N, K, mode):
 
 def test_gemm_rejects_bad_shapes(lib):
     from manual_whisper_b200 import _lib
-    t = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
-    assert lib.mw_gemm_bf16(t.data_ptr(), t.data_ptr(), None, None, t.data_ptr(), 64, 48, 64, 0, 0, _stream()) == 1
+    t = torch.zeros(64, 64, device="cuda", dtype=_h16())
+    assert lib.mw_gemm_h16(t.data_ptr(), t.data_ptr(), None, None, t.data_ptr(), 64, 48, 64, 0, 0, _stream()) == 1
     assert b"multiple of 32" in lib.mw_last_error()
 
 
@@ -57,9 +62,9 @@ def test_encoder_attention(lib, B, T, H):
     dev = torch.device("cuda:0")
     d = H * 64
     g = torch.Generator(device=dev).manual_seed(T)
-    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g).bfloat16()
-    out = torch.zeros(B * T, d, device=dev, dtype=torch.bfloat16)
-    _lib.check(lib.mw_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, T, H, _stream()), "attention")
+    qkv = torch.randn(B * T, 3 * d, device=dev, generator=g).to(_h16())
+    out = torch.zeros(B * T, d, device=dev, dtype=_h16())
+    _lib.check(lib.mw_attention_h16(qkv.data_ptr(), out.data_ptr(), B, T, H, _stream()), "attention")
     q, k, v = [t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(d, dim=1)]
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, d)
     assert (out.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 2e-3
@@ -72,7 +77,7 @@ def test_layernorm(lib, rows, d):
     g = torch.Generator(device=dev).manual_seed(d)
     x = torch.randn(rows, d, device=dev, generator=g) * 3 + 1
     gam, bet = torch.randn(d, device=dev, generator=g), torch.randn(d, device=dev, generator=g)
-    out = torch.empty(rows, d, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(rows, d, device=dev, dtype=_h16())
     _lib.check(lib.mw_layernorm(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), out.data_ptr(), rows, d, _stream()), "ln")
     ref = torch.nn.functional.layer_norm(x, (d,), gam, bet, 1e-5)
-    assert torch.equal(out, ref.bfloat16()) or (out.float() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    assert torch.equal(out, ref.to(_h16())) or (out.float() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()

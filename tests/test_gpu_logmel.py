@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import torch
 
+from manual_whisper_b200 import _lib
+
 from conftest import audio_case
 
 pytestmark = pytest.mark.gpu
@@ -70,11 +72,11 @@ def test_chunked_api_matches_oracle_and_time_major_copy(dev):
     offs = np.array([0, 123457, 1000001, 2000000, N - 5, 500000], dtype=np.int64)
     lens = np.array([480000, 333333, 17, 480000, 5, 0], dtype=np.int32)
     plan = LogMelPlan(128, 0, max_chunks=8)
-    out_t = torch.full((6, 3002, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    out_t = torch.full((6, 3002, 128), 7.0, dtype=_lib.storage_dtype(), device=dev)
     got = plan.chunks(torch.from_numpy(audio).to(dev), torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev), out_t=out_t)
     ref = log_mel_chunks(audio, offs, lens, 128)
     assert (got.cpu() - ref).abs().max().item() < TOL
-    assert torch.equal(out_t[:, 1:3001].float().cpu(), got.cpu().transpose(1, 2).bfloat16().float())
+    assert torch.equal(out_t[:, 1:3001].float().cpu(), got.cpu().transpose(1, 2).to(_lib.storage_dtype()).float())
     assert out_t[:, [0, 3001]].float().abs().max().item() == 0.0
     assert torch.all(got[5] == -1.5)          # empty chunk = silence
     with pytest.raises(ValueError, match="max_chunks"):

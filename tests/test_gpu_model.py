@@ -26,7 +26,7 @@ def small():
     eng = Engine(dims, sd, 0, max_batch=4, max_beam=5)
     g = torch.Generator().manual_seed(9)
     mel = (torch.randn(4, 80, 400, generator=g) * 0.5).clamp(-1.5, 1.5)
-    return dims, scaled_tokens(2048), sd, eng, mel, OracleWhisper(dims, sd), OracleWhisper(dims, sd, emulate_bf16=True)
+    return dims, scaled_tokens(2048), sd, eng, mel, OracleWhisper(dims, sd), OracleWhisper(dims, sd, emulate=True)
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +40,7 @@ def tiny():
     eng = Engine(dims, sd, 0, max_batch=2, max_beam=1)
     g = torch.Generator().manual_seed(3)
     mel = (torch.randn(2, 80, 3000, generator=g) * 0.5).clamp(-1.5, 1.5)
-    return dims, special_tokens(dims.vocab), sd, eng, mel, OracleWhisper(dims, sd), OracleWhisper(dims, sd, emulate_bf16=True)
+    return dims, special_tokens(dims.vocab), sd, eng, mel, OracleWhisper(dims, sd), OracleWhisper(dims, sd, emulate=True)
 
 
 def rel_l2(a, b):
@@ -62,8 +62,8 @@ def test_encoder_within_bf16_tolerance(which, request):
 
 def test_encode_time_major_entry_point_equals_encode(small):
     dims, tok, sd, eng, mel, orc, emu = small
-    t = torch.zeros(mel.shape[0], 402, 80, dtype=torch.bfloat16, device="cuda")
-    t[:, 1:401] = mel.cuda().transpose(1, 2).bfloat16()
+    t = torch.zeros(mel.shape[0], 402, 80, dtype=eng.h16, device="cuda")
+    t[:, 1:401] = mel.cuda().transpose(1, 2).to(eng.h16)
     assert torch.equal(eng.encode_time_major(t), eng.encode(mel.cuda()))
 
 

@@ -15,7 +15,7 @@ def setup():
     tok = scaled_tokens(2048)
     sd = random_init(dims, seed=5, scheme="lively")
     audio, turns = mw.synthetic_speech(200.0, seed=2)
-    pipe = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+    pipe = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1},
                          vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4)
     return mw, dims, tok, sd, audio, turns, pipe
 
@@ -44,7 +44,7 @@ def test_transcribe_matches_oracle_pipeline(setup):
     wins = mw.merge_chunks(turns, 30)
     offs = [int(w["start"] * 16000) for w in wins]
     lens = [int(w["end"] * 16000) - o for w, o in zip(wins, offs)]
-    emu = OracleWhisper(dims, sd, emulate_bf16=True)
+    emu = OracleWhisper(dims, sd, emulate=True)
     prompt = [tok.sot, tok.lang_id("en"), tok.transcribe, tok.no_timestamps]
     same = 0
     with torch.no_grad():
@@ -102,9 +102,9 @@ def test_sharded_helper_single_process(setup):
 def test_batches_in_flight_do_not_change_results(setup):
     """Two shared-weight replicas on two streams (the default) give the ids of a single replica."""
     mw, dims, tok, sd, audio, turns, pipe = setup
-    one = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+    one = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1},
                         vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=1)
-    three = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+    three = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1},
                           vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=3)
     assert len(one.replicas) == 1 and len(three.replicas) == 3
     assert three.replicas[1].engine.weights is three.replicas[0].engine.weights        # one copy of the weights
@@ -114,6 +114,21 @@ def test_batches_in_flight_do_not_change_results(setup):
     assert three.last_stats["replicas"] == 3
 
 
+def test_beam_search_on_concurrent_replicas_matches_single_stream(setup):
+    """Beam 5 (the whisperx default) with 6 batches in flight: the step counter is advanced by a kernel none of whose
+    CTAs reads it, so late-scheduled CTAs of the re-parenting kernel cannot see the next step's position."""
+    mw, dims, tok, sd, audio, turns, pipe = setup
+    kw = dict(compute_type="float16", language="en", asr_options={"beam_size": 5, "without_timestamps": False},
+              vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=2)
+    one = mw.load_model("tiny", "cuda", streams_per_device=1, **kw)
+    six = mw.load_model("tiny", "cuda", streams_per_device=6, **kw)
+    a = one.transcribe(audio, batch_size=2)
+    for _ in range(2):
+        b = six.transcribe(audio, batch_size=2)
+        assert [s["tokens"] for s in a["segments"]] == [s["tokens"] for s in b["segments"]]
+    assert six.last_stats["replicas"] >= 4
+
+
 def test_device_side_vad_front_end(setup):
     """frame energies on the GPU give the same turns as the host VAD and the same transcript."""
     mw, dims, tok, sd, audio, turns, pipe = setup
@@ -121,9 +136,9 @@ def test_device_side_vad_front_end(setup):
     host = mw.EnergyVad()({"waveform": torch.from_numpy(a)[None], "sample_rate": 16000})
     dev = mw.GpuEnergyVad()({"waveform": torch.from_numpy(a).cuda()[None], "sample_rate": 16000})
     assert [(round(s.start, 2), round(s.end, 2)) for s in host] == [(round(s.start, 2), round(s.end, 2)) for s in dev]
-    p_host = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, model=sd,
+    p_host = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1}, model=sd,
                            dims=dims, tokens=tok, max_batch=4, vad_method="energy", streams_per_device=1)
-    p_dev = mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, model=sd,
+    p_dev = mw.load_model("tiny", "cuda", compute_type="float16", language="en", asr_options={"beam_size": 1}, model=sd,
                           dims=dims, tokens=tok, max_batch=4, vad_method="energy_gpu", streams_per_device=1)
     r1, r2 = p_host.transcribe(a, batch_size=4), p_dev.transcribe(a, batch_size=4)
     assert [(s["start"], s["end"], s["tokens"]) for s in r1["segments"]] == [(s["start"], s["end"], s["tokens"]) for s in r2["segments"]]
@@ -133,7 +148,7 @@ def test_device_side_vad_front_end(setup):
 def test_in_process_multi_gpu_replicas(setup):
     """device_index=[0, 1]: one replica set per GPU in one process; batches are dealt out dynamically, order restored."""
     mw, dims, tok, sd, audio, turns, pipe = setup
-    two = mw.load_model("tiny", "cuda", device_index=[0, 1], compute_type="bfloat16", language="en", asr_options={"beam_size": 1},
+    two = mw.load_model("tiny", "cuda", device_index=[0, 1], compute_type="float16", language="en", asr_options={"beam_size": 1},
                         vad_model=mw.InjectedVad(turns), model=sd, dims=dims, tokens=tok, max_batch=4, streams_per_device=2)
     assert sorted({r.device.index for r in two.replicas}) == [0, 1] and len(two.replicas) == 4
     a = pipe.transcribe(audio, batch_size=2)
@@ -149,7 +164,7 @@ def test_load_model_from_safetensors_checkpoint(setup, tmp_path):
     path = tmp_path / "tiny" / "model.safetensors"
     path.parent.mkdir()
     save_file({k: v.contiguous() for k, v in sd.items()}, str(path))
-    kw = dict(compute_type="bfloat16", language="en", asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), dims=dims,
+    kw = dict(compute_type="float16", language="en", asr_options={"beam_size": 1}, vad_model=mw.InjectedVad(turns), dims=dims,
               tokens=tok, max_batch=4)
     by_path = mw.load_model("tiny", "cuda", model=str(path), **kw)
     by_root = mw.load_model("tiny", "cuda", download_root=str(tmp_path), **kw)

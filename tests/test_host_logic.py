@@ -90,9 +90,9 @@ def test_load_model_argument_errors():
     with pytest.raises(ValueError, match="compute type"):
         mw.load_model("tiny", "cuda", compute_type="fp7")
     with pytest.raises(ValueError, match="vad_method"):
-        mw.load_model("tiny", "cuda", compute_type="bfloat16", vad_method="webrtc")
+        mw.load_model("tiny", "cuda", compute_type="float16", vad_method="webrtc")
     with pytest.raises(TypeError, match="unexpected option"):
-        mw.load_model("tiny", "cuda", compute_type="bfloat16", asr_options={"beam": 3})
+        mw.load_model("tiny", "cuda", compute_type="float16", asr_options={"beam": 3})
 
 
 def test_default_options_match_whisperx_defaults():
@@ -144,7 +144,7 @@ def test_load_model_rejects_non_whisper_checkpoint(tmp_path):
     bad = str(tmp_path / "model.safetensors")
     save_file({"foo": torch.zeros(2)}, bad)
     with pytest.raises(ValueError, match="not a Hugging Face Whisper checkpoint"):
-        mw.load_model("tiny", "cuda", compute_type="bfloat16", language="en", model=bad)
+        mw.load_model("tiny", "cuda", compute_type="float16", language="en", model=bad)
 
 
 def test_sinc_resample_kernel_matches_oracle_and_wav_rate_error(tmp_path):
