@@ -181,6 +181,13 @@ mw_status mw_gemm_h16(const void* d_a, const void* d_w, const float* d_bias, con
                        void* d_out, int M, int N, int K, int gelu, int out_f32, void* stream);
 /* encoder self-attention on packed qkv h16 [B*T, 3*d]; out h16 [B*T, d] */
 mw_status mw_attention_h16(const void* d_qkv, void* d_out, int B, int T, int n_heads, void* stream);
+/* The decode-step projection (csrc/decode_gemm.cu): D[R,N] = X[R,K] . W[N,K]^T (+bias) (flags&1: GELU) (+residual f32 [R,N]);
+ * X,W h16; out h16, or f32 when flags&2; R <= 256, K % 64 == 0.  W is streamed once for all R rows. */
+mw_status mw_decode_gemm_h16(const void* d_x, const void* d_w, const float* d_bias, const float* d_residual,
+                             void* d_out, int R, int N, int K, int flags, void* stream);
+/* Measurement hook: d_stamps (device, 8 x uint64) receives %globaltimer at the phase boundaries of CTA (0,0) of the
+ * following mw_decode_gemm_h16 calls; NULL switches it off (scripts/gpu_dg_phases.py). */
+void mw_decode_gemm_debug(unsigned long long* d_stamps);
 mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_h16,
                        int rows, int d, void* stream);
 

@@ -78,6 +78,8 @@ struct DecoderState {
     // host side
     mw::DecCtl* h_ctl = nullptr;         // pinned [2]
     cudaStream_t cap_stream = nullptr;
+    bool use_prio = false;
+    int prio_low = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // step graphs are specific to (rows, beam): a small cache keeps the last few shapes (full batches and the short
     // last batch of a recording alternate) so they are not re-captured on every call
@@ -360,7 +362,14 @@ mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const fl
 }
 
 mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
-                      int ldo, int R, int N, int K, int flags, cudaStream_t st) {
+                      int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg = true) {
+    // R >= MW_DG_MIN_ROWS rows (merged greedy batches): the weight-stationary tcgen05 kernel (decode_gemm.cu) streams W once
+    // for all rows; the mma.sync kernels below re-read it per 32-row block (from L2 after the first block) and stay in charge
+    // of the 32-row batches they were tuned on and of beam search, where they measured faster (a decode
+    // step is a chain of ~360 latency-bound launches, so bytes saved do not buy time unless the launch is also shorter).
+    static const int dg_min_rows = [] { const char* e = getenv("MW_DG_MIN_ROWS"); return e ? atoi(e) : 96; }();
+    if (allow_dg && R >= dg_min_rows && decode_gemm_supported(ldx, ldw, R, N, K))
+        return decode_gemm_launch(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st);
 #define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st)
     MW_SK(5, 8);    // 1280  (large)
     MW_SK(10, 16);  // 5120  (large ffn)
@@ -1253,7 +1262,19 @@ mw_status decoder_state_create(mw_model* m) {
     A((void**)&s->active, B * 4, true);
     if (st != MW_OK) return st;
     MW_CUDA_CHECK(cudaMallocHost((void**)&s->h_ctl, 2 * sizeof(DecCtl)));
-    MW_CUDA_CHECK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    // Experiment hook, OFF unless MW_PRIO=1: capture the step graphs on a HIGH-priority stream and launch the one
+    // bandwidth-hungry kernel of the step (cross-attention) at the LOWEST priority, so that with several batches in flight the
+    // short latency-bound kernels of one batch get SM slots ahead of another batch's queued cross-attention CTAs.  Measured
+    // on the real generate loop (scripts/gpu_generate_concurrent.py): no change (451.2 vs 451.4 ms per batch) - the kernel
+    // classes of concurrent batches already time-slice additively, DESIGN.md section 4.
+    {
+        int least = 0, greatest = 0;
+        MW_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const char* e = getenv("MW_PRIO");
+        s->use_prio = (e && e[0] == '1') && greatest < least;
+        s->prio_low = least;
+        MW_CUDA_CHECK(cudaStreamCreateWithPriority(&s->cap_stream, cudaStreamNonBlocking, s->use_prio ? greatest : least));
+    }
     for (int i = 0; i < 2; ++i) MW_CUDA_CHECK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
     MW_CUDA_CHECK(cudaFuncSetAttribute(decode_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return MW_OK;
@@ -1315,8 +1336,9 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
         auto W = [&](int id) { return m->dlw(l, id); };
         auto F = [&](int id) { return (const float*)m->dlw(l, id); };
         const bool LN = parts & PART_LN, GM = parts & PART_GEMM;
+        const bool dg = beam <= 1;
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st, dg)) != MW_OK) return r;
         if (parts & PART_SELF) {
             mw_h* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
             mw_h* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
@@ -1325,9 +1347,9 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                 s->qkv, 3 * d, kc, vc, d, ctx, idx, ctx, s->ctl, 0, 1, s->qkv + d, s->qkv + 2 * d, 3 * d, s->att, d);
             MW_LAUNCH_CHECK();
         }
-        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg)) != MW_OK) return r;
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st, dg)) != MW_OK) return r;
         if (parts & PART_CROSS) {
             mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             if (beam > 1) {
@@ -1341,14 +1363,26 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                 if (r != MW_OK) return r;
             } else {
                 dim3 grid(c.n_heads, R);
-                cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
-                MW_LAUNCH_CHECK();
+                if (s->use_prio) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = grid; cfg.blockDim = dim3(128, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributePriority;
+                    attr[0].val.priority = s->prio_low;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    MW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, cross_attn_stream_kernel, (const mw_h*)s->qx, d, (const mw_h*)kv,
+                                                     (const mw_h*)(kv + d), (int64_t)(2 * d), T, s->att, d));
+                    count_launch();
+                } else {
+                    cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
+                    MW_LAUNCH_CHECK();
+                }
             }
         }
-        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg)) != MW_OK) return r;
         if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st, dg)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st, dg)) != MW_OK) return r;
     }
     return MW_OK;
 }
@@ -1509,8 +1543,10 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     });
     if (r != MW_OK) { destroy_graph_entry(s->graphs); return r; }
     for (int phase = 0; phase < (beam > 1 ? 2 : 1); ++phase) {
+        // MW_STEP_PARTS (measurement only, results are then meaningless): kernel classes kept in the step graph
+        static const int step_parts = [] { const char* e = getenv("MW_STEP_PARTS"); return e ? atoi(e) : (int)PART_ALL; }();
         r = capture_graph(s, &s->graphs.gen[phase], [&](cudaStream_t st) -> mw_status {
-            mw_status q = enqueue_layers(m, R, beam, phase, st);
+            mw_status q = enqueue_layers(m, R, beam, phase, st, step_parts);
             if (q != MW_OK) return q;
             if ((q = enqueue_logits(m, R, st)) != MW_OK) return q;
             return enqueue_select(m, B, beam, phase, st);

@@ -52,8 +52,10 @@ struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
         cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
+        // always set: on a fresh host thread this is what binds the primary context, which the driver-API tensor-map
+        // encoder needs (a thread whose first call into the library is mw_generate got CUDA_ERROR_INVALID_CONTEXT)
+        cudaSetDevice(dev);
+        if (prev == dev) prev = -1;
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };

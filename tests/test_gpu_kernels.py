@@ -49,6 +49,41 @@ def test_gemm(lib, M, N, K, mode):
     assert (out.float() - ref).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("R,N,K", [(32, 1280, 1280), (17, 384, 384), (64, 3840, 1280), (68, 1280, 5120), (128, 5120, 1280),
+                                   (128, 1280, 1280), (136, 1280, 1280), (256, 1280, 5120), (200, 51866, 1280), (1, 128, 128),
+                                   (96, 51865, 384), (33, 2048, 128), (128, 300, 192)])
+@pytest.mark.parametrize("mode", ["plain_f32", "bias_gelu", "bias_resid_f32"])
+def test_decode_gemm(lib, R, N, K, mode):
+    """The weight-stationary decode GEMM (swap-AB tcgen05, cluster split-K) against torch fp32; deterministic across runs."""
+    from manual_whisper_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(R * 7 + N)
+    x = (torch.randn(R, K, device=dev, generator=g) * 0.5).to(_h16())
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).to(_h16())
+    bias = torch.randn(N, device=dev, generator=g) if mode != "plain_f32" else None
+    res = torch.randn(R, N, device=dev, generator=g) if mode == "bias_resid_f32" else None
+    f32 = mode != "bias_gelu"
+    flags = (1 if mode == "bias_gelu" else 0) | (2 if f32 else 0)
+    outs = []
+    for _ in range(2):
+        out = torch.full((R, N), 7.0, device=dev, dtype=torch.float32 if f32 else _h16())
+        _lib.check(lib.mw_decode_gemm_h16(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                          res.data_ptr() if res is not None else None, out.data_ptr(), R, N, K, flags, _stream()),
+                   "mw_decode_gemm_h16")
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    ref = x.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if mode == "bias_gelu":
+        ref = torch.nn.functional.gelu(ref)
+    if res is not None:
+        ref = ref + res
+    tol = 2e-4 * ref.abs().max().item() if f32 else 2 ** -8 * ref.abs().max().item() + 1e-3
+    assert (outs[0].float() - ref).abs().max().item() <= tol
+
+
 def test_gemm_rejects_bad_shapes(lib):
     from manual_whisper_b200 import _lib
     t = torch.zeros(64, 64, device="cuda", dtype=_h16())
