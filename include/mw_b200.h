@@ -185,6 +185,10 @@ mw_status mw_attention_h16(const void* d_qkv, void* d_out, int B, int T, int n_h
  * X,W h16; out h16, or f32 when flags&2; R <= 256, K % 64 == 0.  W is streamed once for all R rows. */
 mw_status mw_decode_gemm_h16(const void* d_x, const void* d_w, const float* d_bias, const float* d_residual,
                              void* d_out, int R, int N, int K, int flags, void* stream);
+/* Measurement hook (bench.py "in_step"): keep only the kernel classes in `parts` (the mask of mw_bench_step, plus 64 = token
+ * selection) in decode-step graphs captured from now on, process-wide; 127 restores the real step.  Ids are meaningless while a
+ * class is missing; the change in step time is that class's cost inside the real, concurrent step. */
+void mw_debug_step_parts(int parts);
 /* Measurement hook: d_stamps (device, 8 x uint64) receives %globaltimer at the phase boundaries of CTA (0,0) of the
  * following mw_decode_gemm_h16 calls; NULL switches it off (scripts/gpu_dg_phases.py). */
 void mw_decode_gemm_debug(unsigned long long* d_stamps);

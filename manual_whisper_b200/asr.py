@@ -135,7 +135,7 @@ class WhisperModel:
         results = self.engine.generate(enc, prompt, self.tokens, beam_size=options.beam_size, patience=options.patience,
                                        length_penalty=options.length_penalty, max_length=self.max_length,
                                        suppress_blank=options.suppress_blank, suppress_tokens=options.suppress_tokens,
-                                       forced_eot_len=forced_eot_len)
+                                       without_timestamps=options.without_timestamps, forced_eot_len=forced_eot_len)
         tokens_batch = [r.sequences_ids[0] for r in results]
         text = tokenizer.decode_batch([[t for t in tk if t < tokenizer.eot] for tk in tokens_batch])
         return text, tokens_batch
@@ -155,7 +155,9 @@ class FasterWhisperPipeline:
 
     def __init__(self, model: Union[WhisperModel, List[WhisperModel]], vad, vad_params: dict, options: TranscriptionOptions,
                  tokenizer: Optional[Tokenizer] = None, device: Union[int, str, torch.device] = -1,
-                 framework: str = "pt", language: Optional[str] = None, suppress_numerals: bool = False, **kwargs):
+                 framework: str = "pt", language: Optional[str] = None, suppress_numerals: bool = False,
+                 hf_tokenizer=None, **kwargs):
+        self.hf_tokenizer = hf_tokenizer if hf_tokenizer is not None else getattr(tokenizer, "hf", None)
         self.replicas: List[WhisperModel] = list(model) if isinstance(model, (list, tuple)) else [model]
         self.model = self.replicas[0]
         self.tokenizer = tokenizer
@@ -233,12 +235,14 @@ class FasterWhisperPipeline:
         if self.tokenizer is None:
             language = language or self.detect_language(audio)
             task = task or "transcribe"
-            self.tokenizer = Tokenizer(self.model.tokens, self.model.is_multilingual, task=task, language=language)
+            self.tokenizer = Tokenizer(self.model.tokens, self.model.is_multilingual, task=task, language=language,
+                                       hf=self.hf_tokenizer)
         else:
             language = language or self.tokenizer.language_code
             task = task or self.tokenizer.task_name
             if task != self.tokenizer.task_name or language != self.tokenizer.language_code:
-                self.tokenizer = Tokenizer(self.model.tokens, self.model.is_multilingual, task=task, language=language)
+                self.tokenizer = Tokenizer(self.model.tokens, self.model.is_multilingual, task=task, language=language,
+                                           hf=self.hf_tokenizer)
         return language, task
 
     def transcribe_windows_host(self, audio: np.ndarray, vad_segments: List[Dict], batch_size: Optional[int] = None,
@@ -393,7 +397,10 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
     ``streams_per_device`` replicas per GPU share one copy of the weights and keep that many batches in flight.
     """
     if whisper_arch.endswith(".en"):
-        language = "en"
+        # English-only checkpoints have their own vocabulary (51864 ids, <|endoftext|> 50256, no language/task tokens in the
+        # sot sequence); running one with the multilingual control ids would be silently wrong, so it is refused
+        raise ValueError(f"'{whisper_arch}': English-only checkpoints are not supported by this engine; the reference exposes "
+                         "the multilingual sizes tiny / base / small / medium / large-v3 (/root/reference/README.md:85)")
     dev = torch.device(device) if not isinstance(device, torch.device) else device
     if dev.type != "cuda":
         raise ValueError(f"unsupported device {device!r}: the B200-native engine has no CPU path; pass device='cuda'")
@@ -450,8 +457,12 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
                                              tokens=toks, share_weights_with=first))
 
     tokenizer = None
+    hf_tokenizer = None
+    if tokenizer_file:
+        import tokenizers
+        hf_tokenizer = tokenizers.Tokenizer.from_file(tokenizer_file)
     if language is not None:
-        tokenizer = Tokenizer(toks, True, task=task, language=language, tokenizer_file=tokenizer_file)
+        tokenizer = Tokenizer(toks, True, task=task, language=language, hf=hf_tokenizer)
     else:
         print("No language specified, language will be first be detected for each audio file (increases inference time).")
 
@@ -466,4 +477,5 @@ def load_model(whisper_arch: str, device: str, device_index=0, compute_type: str
         vad_model = cls(vad_onset=default_vad_options["vad_onset"], vad_offset=default_vad_options["vad_offset"],
                         chunk_size=default_vad_options["chunk_size"])
     return FasterWhisperPipeline(model=replicas, vad=vad_model, options=default_asr_options, tokenizer=tokenizer,
-                                 language=language, suppress_numerals=suppress_numerals, vad_params=default_vad_options)
+                                 language=language, suppress_numerals=suppress_numerals, vad_params=default_vad_options,
+                                 hf_tokenizer=hf_tokenizer)

@@ -58,7 +58,7 @@ _ALIASES = {"large": "large-v3", "large-v1": "large-v2"}
 def model_dims(name: str) -> ModelDims:
     key = _ALIASES.get(name, name)
     if key.endswith(".en"):
-        key = key[:-3]
+        raise ValueError(f"'{name}': English-only checkpoints (vocab 51864, their own control-token ids) are not supported")
     if key not in _DIMS:
         raise ValueError(f"Invalid model size '{name}', expected one of: {', '.join(sorted(_DIMS))}")
     return ModelDims(key, *_DIMS[key])

@@ -79,6 +79,7 @@ struct DecoderState {
     mw::DecCtl* h_ctl = nullptr;         // pinned [2]
     cudaStream_t cap_stream = nullptr;
     bool use_prio = false;
+    int parts_epoch = 0;
     int prio_low = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // step graphs are specific to (rows, beam): a small cache keeps the last few shapes (full batches and the short
@@ -1518,9 +1519,16 @@ mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st)
 
 int launches_per_layers(const mw_model_config& c) { return 1 + c.dec_layers * 11; }
 
+std::atomic<int> g_step_parts{[] { const char* e = getenv("MW_STEP_PARTS"); return e ? atoi(e) : (int)PART_ALL; }()};
+std::atomic<int> g_step_parts_epoch{0};
+
 mw_status ensure_graphs(mw_model* m, int B, int beam) {
     DecoderState* s = m->dec;
     const int R = B * beam;
+    if (s->parts_epoch != g_step_parts_epoch.load()) {      // the kept classes changed: cached graphs are stale
+        destroy_graphs(s);
+        s->parts_epoch = g_step_parts_epoch.load();
+    }
     DecoderState::Graphs* slot = nullptr;
     for (auto& g : s->graph_cache)
         if (g.prefill && g.R == R && g.beam == beam) { g.last_use = ++s->graph_clock; s->graphs = g; return MW_OK; }
@@ -1543,8 +1551,8 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     });
     if (r != MW_OK) { destroy_graph_entry(s->graphs); return r; }
     for (int phase = 0; phase < (beam > 1 ? 2 : 1); ++phase) {
-        // MW_STEP_PARTS (measurement only, results are then meaningless): kernel classes kept in the step graph
-        static const int step_parts = [] { const char* e = getenv("MW_STEP_PARTS"); return e ? atoi(e) : (int)PART_ALL; }();
+        // measurement only (mw_debug_step_parts / MW_STEP_PARTS; ids are then meaningless): kernel classes kept in the step graph
+        const int step_parts = g_step_parts.load();
         r = capture_graph(s, &s->graphs.gen[phase], [&](cudaStream_t st) -> mw_status {
             mw_status q = enqueue_layers(m, R, beam, phase, st, step_parts);
             if (q != MW_OK) return q;
@@ -1880,4 +1888,12 @@ extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, flo
     cudaGraphExecDestroy(g);
     *h_ms_avg = ms / iters;
     return MW_OK;
+}
+
+// ---- measurement hook (bench.py "in_step" attribution): keep only the kernel classes in `parts` (mask of mw_bench_step) in
+// the decode-step graphs captured from now on, process-wide; 127 restores the real step.  Decoded ids are meaningless while a
+// class is missing: the difference in step time with and without a class is its in-step cost under real concurrency.
+extern "C" void mw_debug_step_parts(int parts) {
+    mw::g_step_parts.store(parts);
+    mw::g_step_parts_epoch.fetch_add(1);
 }

@@ -1,8 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, windows sharded by batch, host gather (no data-path collective).
 
 VAD windows are independent units (same fixed prompt, no cross-window state: SURVEY.md §8e), so the N>1 path
-is: every rank computes the same window list, takes the batches ``rank, rank+world, ...``, transcribes them on
-its own GPU, and the (index, result) pairs are gathered and restored to window order.  torch.distributed is
+is: every rank computes the same window list, takes its share of the windows (longest-first bin packing, equal counts),
+transcribes them on its own GPU, and the (index, result) pairs are gathered and restored to window order.  torch.distributed is
 used only for that final object gather (NCCL or gloo — identical code path, which is what the CPU tests run).
 """
 from __future__ import annotations
@@ -38,24 +38,57 @@ def gather_ordered(local: Sequence[Tuple[int, Any]], n_windows: int, group=None)
     return out
 
 
-def transcribe_sharded(pipeline, audio, batch_size: int, rank: int, world: int, group=None, **kwargs):
-    """model.transcribe across `world` single-GPU processes: same return value on every rank."""
+def shard_windows(lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Window indices owned by each rank: longest-first greedy bin packing (LPT) on window length with equal counts as the
+    first criterion - every window costs the same encoder pass and (at the token cap) the same decode steps, so ranks must
+    hold the same NUMBER of windows before their audio seconds are balanced.  Deterministic; indices
+    of a rank are returned in window order."""
+    if world <= 0:
+        raise ValueError("bad sharding arguments")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    shards: List[List[int]] = [[] for _ in range(world)]
+    load = [0] * world
+    for i in order:
+        r = min(range(world), key=lambda k: (len(shards[k]), load[k], k))
+        shards[r].append(i)
+        load[r] += int(lengths[i])
+    return [sorted(sh) for sh in shards]
+
+
+def sharded_windows(pipeline, audio, chunk_size: int = 30):
+    """The window list every rank computes identically (VAD -> merge_chunks), with sample offsets and lengths."""
     import numpy as np
+    import torch
     from .vad import merge_chunks
     from .config import SAMPLE_RATE
-    import torch
-    audio = np.ascontiguousarray(audio, dtype=np.float32)
     turns = pipeline.vad_model({"waveform": torch.from_numpy(audio).unsqueeze(0), "sample_rate": SAMPLE_RATE})
-    windows = merge_chunks(turns, kwargs.get("chunk_size", 30), onset=pipeline._vad_params["vad_onset"],
-                           offset=pipeline._vad_params["vad_offset"])
-    mine = shard_batches(len(windows), batch_size, world, rank)
+    windows = merge_chunks(turns, chunk_size, onset=pipeline._vad_params["vad_onset"], offset=pipeline._vad_params["vad_offset"])
+    offs = np.clip(np.array([int(w["start"] * SAMPLE_RATE) for w in windows], dtype=np.int64), 0, len(audio))
+    ends = np.clip(np.array([int(w["end"] * SAMPLE_RATE) for w in windows], dtype=np.int64), offs, len(audio))
+    return windows, offs, (ends - offs)
+
+
+def transcribe_sharded(pipeline, audio, batch_size: int, rank: int, world: int, group=None, **kwargs):
+    """model.transcribe across `world` single-GPU processes: same return value on every rank.
+
+    Every rank computes the same window list, takes its LPT share (shard_windows), uploads the span of audio its windows
+    cover ONCE and hands all of its batches to the replicas of its GPU in one call (so the streams_per_device batches in
+    flight are used exactly as in the single-process path); only the final (index, segment) gather crosses ranks."""
+    import numpy as np
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    windows, offs, lens = sharded_windows(pipeline, audio, kwargs.pop("chunk_size", 30))
+    mine = shard_windows(lens, world)[rank]
     local = []
-    for a, b in mine:
-        res = pipeline.transcribe_windows_host(audio, windows[a:b], batch_size=batch_size, **kwargs)
-        for k, seg in enumerate(res):
-            local.append((a + k, seg))
+    language = kwargs.get("language")
+    if mine:
+        res = pipeline.transcribe_windows_host(audio, [windows[i] for i in mine], batch_size=batch_size, **kwargs)
+        local = list(zip(mine, res))
+    if pipeline.tokenizer is not None:
+        language = pipeline.tokenizer.language_code
     segs = gather_ordered(local, len(windows), group)
-    return {"segments": segs, "language": kwargs.get("language") or pipeline.preset_language}
+    if pipeline.preset_language is None:
+        pipeline.tokenizer = None
+    return {"segments": segs, "language": language or pipeline.preset_language}
 
 
 def align_sharded(transcript, model_a, metadata, audio, rank: int, world: int, group=None, *, batch_size: int = 16,

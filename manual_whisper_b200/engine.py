@@ -79,6 +79,15 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, device: torch.dev
     return out
 
 
+def timestamps_enabled(prompt: Sequence[int], tokens: SpecialTokens, without_timestamps: Optional[bool] = None) -> bool:
+    """Whether the timestamp logit rules apply to a generate call."""
+    if without_timestamps is None:
+        prompt = list(prompt)
+        tail = prompt[prompt.index(tokens.sot):] if tokens.sot in prompt else prompt
+        without_timestamps = tokens.no_timestamps in tail
+    return not without_timestamps
+
+
 @dataclass
 class GenerationResult:
     """Mirror of ctranslate2.models.WhisperGenerationResult (the fields whisperx reads)."""
@@ -157,13 +166,16 @@ class Engine:
                  patience: float = 1.0, length_penalty: float = 1.0, max_length: int = 448,
                  suppress_blank: bool = True, suppress_tokens: Optional[Sequence[int]] = (-1,),
                  max_initial_timestamp_index: int = 50, num_hypotheses: int = 1,
-                 forced_eot_len: int = 0) -> List[GenerationResult]:
+                 forced_eot_len: int = 0, without_timestamps: Optional[bool] = None) -> List[GenerationResult]:
+        """`without_timestamps` (what the caller's options say) decides whether the timestamp rules apply; when it is not
+        given, the rules are off iff <|notimestamps|> appears in the prompt after <|startoftranscript|> - NOT just as its last
+        token, because faster-whisper's get_prompt appends `prefix` tokens after it."""
         assert enc.is_cuda and enc.dtype == self.h16 and enc.is_contiguous()
         B = enc.shape[0]
         prompt = [int(t) for t in prompt]
         if not prompt:
             raise ValueError("prompt must not be empty")
-        with_ts = prompt[-1] != tokens.no_timestamps
+        with_ts = timestamps_enabled(prompt, tokens, without_timestamps)
         sup = set()
         for t in suppress_tokens or []:
             if t == -1:

@@ -15,13 +15,13 @@ from .config import SpecialTokens, LANGUAGES
 
 class Tokenizer:
     def __init__(self, tokens: SpecialTokens, multilingual: bool = True, task: Optional[str] = "transcribe",
-                 language: Optional[str] = "en", tokenizer_file: Optional[str] = None):
+                 language: Optional[str] = "en", tokenizer_file: Optional[str] = None, hf=None):
         self.tokens = tokens
         self.multilingual = multilingual
         self.task_name = task
         self.language_code = language
-        self.hf = None
-        if tokenizer_file:
+        self.hf = hf                      # an already loaded tokenizers.Tokenizer (the pipeline keeps one and re-uses it)
+        if self.hf is None and tokenizer_file:
             import tokenizers
             self.hf = tokenizers.Tokenizer.from_file(tokenizer_file)
         if multilingual:
@@ -57,6 +57,10 @@ class Tokenizer:
     def encode(self, text: str) -> List[int]:
         if self.hf is not None:
             return self.hf.encode(text, add_special_tokens=False).ids
+        if text.strip():
+            import warnings
+            warnings.warn("no tokenizer.json is loaded: text (initial_prompt / hotwords / prefix) is encoded one id per UTF-8 "
+                          "byte, which is NOT the Whisper BPE; pass tokenizer_file= to load_model for real prompts", stacklevel=2)
         return [b for b in text.encode("utf-8")]     # placeholder: one id per byte (ids 0..255)
 
     def decode(self, ids: Sequence[int]) -> str:

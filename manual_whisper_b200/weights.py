@@ -63,13 +63,19 @@ def _keys(dims: ModelDims):
 
 # "peaked" scheme: std of the token embedding per model width, chosen (scripts/parity_probe.py) so that the tied output
 # projection's self-similarity term E[cur].E[cur] stands about 1.25x above the largest of the other ~51 k logits
-PEAKED_EMB_STD = {384: 1.0, 512: 1.0, 768: 1.0, 1024: 1.0, 1280: 1.0}
+PEAKED_EMB_STD = {384: 0.15, 512: 0.14, 768: 0.13, 1024: 0.12, 1280: 0.11}
 
 
 def random_init(dims: ModelDims, seed: int = 1234, scheme: str = "survey", emb_std: float = None) -> Dict[str, torch.Tensor]:
     """Seeded weights, fp32 tensors holding values the engine's 16-bit storage represents exactly.
 
     scheme "survey": N(0, 0.02^2) matrices/embeddings/biases, LayerNorm gamma=1 beta=0.
+    scheme "peaked": "lively" with a wider token embedding (PEAKED_EMB_STD).  Because the output projection is tied to the
+    embedding, the current token's own embedding then stands out in the logits (E[cur].E[cur] against ~51 k cross terms) the
+    way a trained decoder's prediction does: the fp32 oracle's top-2 margin has a median of 2-3 nats with < 0.5 % of the
+    steps under 0.05 nat (profiles/parity_probe_r2.json), instead of the near-ties of an untrained Gaussian projection,
+    while the audio still switches the decoded token a few times per window.  It is what makes the north-star bar "ids
+    identical on >= 99 % of windows" testable on random-init weights; both sides get the same values.
     scheme "lively": fan-in scaled matrices (std = gain/sqrt(fan_in)), wider embeddings, randomised
     LayerNorm affine and biases, so attention is not uniform and the decoded ids depend on the
     audio; documented in DESIGN.md and used identically by the oracle and the engine.

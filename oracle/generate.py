@@ -112,7 +112,10 @@ def generate(model, enc: torch.Tensor, prompt: List[int], tok, opt: GenOptions,
     (and, with return_trace, per-step fp32 masked logits of the greedy path for margin analysis)."""
     B = enc.shape[0]
     P = len(prompt)
-    with_ts = not (P > 0 and prompt[-1] == tok.no_timestamps)
+    # timestamp rules are off iff <|notimestamps|> follows <|startoftranscript|> in the prompt (get_prompt appends `prefix`
+    # tokens AFTER it, so looking only at the last prompt token would switch the rules on for prefixed prompts)
+    tail = prompt[prompt.index(tok.sot):] if tok.sot in prompt else prompt
+    with_ts = tok.no_timestamps not in tail
     suppress = expand_suppress(tok, opt.suppress_tokens, with_ts)
     sup_begin = list(tok.suppress_ids_begin) if opt.suppress_blank else []
     n_new = max_new_tokens(P, opt.max_length)

@@ -38,7 +38,13 @@ def _r(x: torch.Tensor, on) -> torch.Tensor:
 
 
 class OracleWhisper:
-    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate=False):
+    def __init__(self, dims, sd: Dict[str, torch.Tensor], emulate=False, int8: bool = False):
+        """int8=True: every Linear (and the tied output projection) runs as a dynamically quantised int8 GEMM - int8 weights
+        with per-output-row scales, activations quantised per call, int32 accumulation, fp32 out; convolutions, LayerNorm,
+        softmax, GELU and residuals stay fp32.  That is the arithmetic of CTranslate2's compute_type="int8" on CPU (SURVEY.md
+        A.9), the mode the reference ships (/root/reference/transcribe.py:30-32); used by bench.py's CPU legs only."""
+        self.int8 = int8
+        self._packed = {}
         self.dims = dims
         self.sd = {k: v.to(torch.float32) for k, v in sd.items()}
         self.emu = engine_rounding() if emulate is True else emulate
@@ -48,8 +54,21 @@ class OracleWhisper:
     def _ln(self, x, prefix):
         return F.layer_norm(x, (x.shape[-1],), self.sd[prefix + ".weight"], self.sd[prefix + ".bias"], 1e-5)
 
+    def _qlinear(self, x, key, w, b):
+        packed = self._packed.get(key)
+        if packed is None:
+            scales = (w.abs().amax(dim=1).clamp_min(1e-12) / 127.0).to(torch.float64)
+            qw = torch.quantize_per_channel(w, scales, torch.zeros(w.shape[0], dtype=torch.int64), 0, torch.qint8)
+            packed = self._packed[key] = torch.ops.quantized.linear_prepack(qw, b)
+        shape = x.shape
+        y = torch.ops.quantized.linear_dynamic(x.reshape(-1, shape[-1]).contiguous(), packed, reduce_range=False)
+        return y.reshape(*shape[:-1], w.shape[0])
+
     def _lin(self, x, prefix, bias=True):
-        return F.linear(x, self.sd[prefix + ".weight"], self.sd.get(prefix + ".bias") if bias else None)
+        w, b = self.sd[prefix + ".weight"], (self.sd.get(prefix + ".bias") if bias else None)
+        if self.int8:
+            return self._qlinear(x, prefix, w, b)
+        return F.linear(x, w, b)
 
     def _heads(self, x):  # [B,T,d] -> [B,H,T,64]
         B, T, _ = x.shape
@@ -146,6 +165,8 @@ class OracleWhisper:
             h = _r(F.gelu(self._lin(h, p + "fc1")), emu)
             x = x + self._lin(h, p + "fc2")
         h = _r(self._ln(x, "model.decoder.layer_norm"), emu)
+        if self.int8:
+            return self._qlinear(h, "proj_out", sd["model.decoder.embed_tokens.weight"], None)
         return F.linear(h, sd["model.decoder.embed_tokens.weight"])
 
     @staticmethod

@@ -164,3 +164,53 @@ def test_sinc_resample_kernel_matches_oracle_and_wav_rate_error(tmp_path):
     if not torch.cuda.is_available() and not __import__("shutil").which("ffmpeg"):
         with pytest.raises(RuntimeError, match="GPU decoder"):
             mw.load_audio(p)
+
+
+def test_english_only_checkpoints_are_refused():
+    import manual_whisper_b200 as mw
+    from manual_whisper_b200.config import model_dims
+    with pytest.raises(ValueError, match="English-only"):
+        model_dims("small.en")
+    with pytest.raises(ValueError, match="English-only"):
+        mw.load_model("tiny.en", "cuda")
+
+
+def test_timestamp_rules_follow_the_option_not_the_last_prompt_token():
+    from manual_whisper_b200.engine import timestamps_enabled
+    from manual_whisper_b200.config import special_tokens
+    tok = special_tokens(51866)
+    base = [tok.sot, tok.sot + 1, tok.transcribe]
+    assert timestamps_enabled(base, tok) is True
+    assert timestamps_enabled(base + [tok.no_timestamps], tok) is False
+    prefixed = base + [tok.no_timestamps, 400, 401, 402]                      # get_prompt(prefix=...) appends after <|notimestamps|>
+    assert timestamps_enabled(prefixed, tok) is False
+    assert timestamps_enabled(prefixed, tok, without_timestamps=False) is True     # an explicit option wins
+    assert timestamps_enabled([tok.sot_prev, tok.no_timestamps] + base, tok) is True   # only the part after <sot> counts
+
+
+def test_pipeline_keeps_the_loaded_vocabulary_for_every_tokenizer(tmp_path):
+    """tokenizer_file is loaded once and re-used whenever the pipeline rebuilds its Tokenizer (language=None or a call with
+    another language); without one, encoding text warns that it is not the Whisper BPE."""
+    import tokenizers
+    from tokenizers import models, pre_tokenizers
+    from manual_whisper_b200.asr import FasterWhisperPipeline, TranscriptionOptions
+    from manual_whisper_b200.tokenizer import Tokenizer
+    from manual_whisper_b200.config import special_tokens
+    t = tokenizers.Tokenizer(models.WordLevel({"hello": 5, "world": 6, "[UNK]": 0}, unk_token="[UNK]"))
+    t.pre_tokenizer = pre_tokenizers.Whitespace()
+    path = str(tmp_path / "tokenizer.json")
+    t.save(path)
+    tok = special_tokens(51865)
+
+    class _M:
+        tokens = tok
+        is_multilingual = True
+        device = "cpu"
+    hf = tokenizers.Tokenizer.from_file(path)
+    pipe = FasterWhisperPipeline(model=_M(), vad=None, vad_params={}, options=TranscriptionOptions(), tokenizer=None, hf_tokenizer=hf)
+    pipe._prepare_tokenizer(None, "en", None)
+    assert pipe.tokenizer.hf is hf and pipe.tokenizer.encode("hello world") == [5, 6]
+    pipe._prepare_tokenizer(None, "zh", None)                                    # language change rebuilds the Tokenizer
+    assert pipe.tokenizer.language_code == "zh" and pipe.tokenizer.hf is hf
+    with pytest.warns(UserWarning, match="NOT the Whisper BPE"):
+        assert Tokenizer(tok, True, language="en").encode("hi") == [104, 105]
