@@ -7,7 +7,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libmw_b200.so"
+import os
+
+# MW_STORAGE_BF16=1 selects the bf16-storage A/B build (python -m manual_whisper_b200.build under the same variable)
+_LIB_PATH = Path(__file__).resolve().parent / ("libmw_b200_bf16.so" if os.environ.get("MW_STORAGE_BF16") == "1" else "libmw_b200.so")
 _lib = None
 
 c_i32p = C.POINTER(C.c_int32)

@@ -40,15 +40,15 @@ def _newest_header() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """MW_STORAGE_BF16=1 in the environment builds the bf16-storage variant (A/B runs; default is fp16)."""
+    """MW_STORAGE_BF16=1 in the environment builds the bf16-storage variant next to the default fp16 one
+    (libmw_b200_bf16.so, objects in build/obj_bf16; manual_whisper_b200/_lib.py loads it under the same variable): A/B runs."""
+    global OBJ, LIB
     nvcc = _nvcc()
+    bf16 = os.environ.get("MW_STORAGE_BF16") == "1"
+    OBJ = REPO / "build" / ("obj_bf16" if bf16 else "obj")
+    LIB = PKG / ("libmw_b200_bf16.so" if bf16 else "libmw_b200.so")
     OBJ.mkdir(parents=True, exist_ok=True)
-    variant = "bf16" if os.environ.get("MW_STORAGE_BF16") == "1" else "fp16"
-    stamp = OBJ / "variant.txt"
-    if not stamp.exists() or stamp.read_text() != variant:
-        force = True
-        stamp.write_text(variant)
-    extra = ["-DMW_STORAGE_BF16"] if variant == "bf16" else []
+    extra = ["-DMW_STORAGE_BF16"] if bf16 else []
     srcs = sorted(CSRC.glob("*.cu"))
     hdr = max(_newest_header(), Path(__file__).stat().st_mtime)
     jobs = []

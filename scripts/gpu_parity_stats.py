@@ -24,11 +24,13 @@ from scripts.make_parity_fixture import fixture_path, inputs      # noqa: E402
 def engine_ids(meta, n_windows, batch=32, pipe=None):
     """ids the engine decodes for the first n_windows windows of the fixture's recording -> (ids [n, max_new] padded -1, pipe)"""
     import manual_whisper_b200 as mw
+    beam, with_ts, language = meta.get("beam", 1), meta.get("with_timestamps", False), meta.get("language", "zh")
     dims, tok, sd, audio, wins, offs, lens, prompt = inputs(meta["model"], meta["scheme"], meta["windows"], meta["weight_seed"],
-                                                            meta["audio_seed"], meta.get("emb_std"))
+                                                            meta["audio_seed"], meta.get("emb_std"), language, with_ts)
     assert prompt == meta["prompt"]
     if pipe is None:
-        pipe = mw.load_model(meta["model"], "cuda", compute_type="float16", language="zh", asr_options={"beam_size": 1},
+        pipe = mw.load_model(meta["model"], "cuda", compute_type="float16", language=language,
+                             asr_options={"beam_size": beam, "without_timestamps": not with_ts},
                              vad_model=mw.InjectedVad([]), model=sd, max_batch=batch, streams_per_device=1)
     resident = pipe.upload(audio, offs[:n_windows], lens[:n_windows])
     res = pipe.run_device_batches(resident, offs[:n_windows], lens[:n_windows].astype(np.int32), batch)
@@ -49,7 +51,7 @@ def compare(got, ref, margins, forced_len=None):
         if np.array_equal(a, b):
             continue
         k = int(np.nonzero(a != b)[0][0])
-        div.append({"window": w, "step": k, "oracle_margin": float(margins[w, k])})
+        div.append({"window": w, "step": k, "oracle_margin": float(margins[w, k]) if k < margins.shape[1] else float("nan")})
     return {"identical": n - len(div), "of": n, "fraction": (n - len(div)) / n, "divergences": div}
 
 
@@ -59,16 +61,21 @@ def main():
     ap.add_argument("--scheme", default="peaked")
     ap.add_argument("--windows", type=int, default=0)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--tag", default="", help="fixture suffix, e.g. _beam5_ts")
+    ap.add_argument("--batch", type=int, default=32)
     args = ap.parse_args()
-    fx = np.load(fixture_path(args.model, args.scheme))
+    fx = np.load(fixture_path(args.model, args.scheme, args.tag))
     meta = json.loads(str(fx["meta"]))
     n = args.windows or meta["windows"]
-    got, offs, lens, pipe = engine_ids(meta, n)
+    got, offs, lens, pipe = engine_ids(meta, n, batch=args.batch)
     assert np.array_equal(offs[:n], fx["offs"][:n]) and np.array_equal(lens[:n], fx["lens"][:n]), "window table differs from the fixture"
     margins = fx["margins"].astype(np.float32)[:n]
     valid = margins[~np.isnan(margins)]
+    if valid.size == 0:
+        valid = np.array([np.nan], dtype=np.float32)
     from manual_whisper_b200 import _lib
-    out = {"model": args.model, "scheme": args.scheme, "windows": n, "max_new": meta["max_new"],
+    out = {"model": args.model, "scheme": args.scheme, "windows": n, "max_new": meta["max_new"], "beam": meta.get("beam", 1),
+           "with_timestamps": meta.get("with_timestamps", False), "batch": args.batch,
            "engine_storage": "bf16" if _lib.load().mw_storage_dtype() == 1 else "fp16",
            "oracle_margin_nats": {"median": float(np.median(valid)), "share_under_0.05": float((valid < 0.05).mean()),
                                   "share_under_0.01": float((valid < 0.01).mean())},
