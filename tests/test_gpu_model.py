@@ -4,15 +4,33 @@ Stated tolerances (BASELINE.json north_star: "encoder output within stated bf16 
 on >= 99 % of chunks with divergences logged"):
   * encoder output: relative L2 error <= 2e-2 against the fp32 oracle (bf16 operands, fp32 accumulation).
   * teacher-forced decoder logits: max abs error <= 1.5 % of the largest |logit| against the fp32 oracle.
-  * greedy / beam ids: identical to the bf16-rounding oracle, except that a window may diverge at a step where the
-    oracle's own top-2 margin is below NEAR_TIE (the measured bf16 logit noise); such divergences are logged.
+  * greedy / beam ids on the "lively" weights (Gaussian-like logits, margins down to 1e-3): identical to the storage-rounding
+    oracle, except that a window may diverge at a step where the oracle's own top-2 margin is below a DERIVED noise bound:
+    8 sigma of the difference of two logits, sigma = the RMS error of the engine's teacher-forced logits against the same
+    oracle measured in the same session (near_tie_bound below; ~2e-3 with fp16 storage).  Divergences are logged with their
+    margin.  The literal bar - no exemption at all, >= 99 % of >= 128 windows - is tests/test_gpu_parity.py.
 """
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-NEAR_TIE = 0.03
+_BOUNDS = {}
+
+
+def near_tie_bound(which, fx):
+    """8 x sqrt(2) x RMS(engine logits - rounding-oracle logits): the margin below which a flipped argmax is noise."""
+    if which not in _BOUNDS:
+        dims, tok, sd, eng, mel, orc, emu = fx
+        enc = eng.encode(mel.cuda())
+        toks = np.random.default_rng(5).integers(0, min(dims.vocab, tok.eot), size=(mel.shape[0], 12)).astype(np.int32)
+        got = eng.decoder_logits(enc, toks).cpu()
+        with torch.no_grad():
+            ref = emu.decode(torch.from_numpy(toks).long(), 0, emu.cross_kv(enc.float().cpu()), emu.new_cache())
+        rms = (got - ref).pow(2).mean().sqrt().item()
+        _BOUNDS[which] = 8.0 * (2.0 ** 0.5) * rms
+        print(f"[near-tie bound {which}] logit rms error {rms:.2e} -> bound {_BOUNDS[which]:.2e} (logit std {ref.std().item():.2f})")
+    return _BOUNDS[which]
 
 
 @pytest.fixture(scope="module")
@@ -109,8 +127,9 @@ def test_greedy_ids(which, with_ts, request):
         ref, trace = generate(emu, enc.float().cpu(), prompt, tok, GenOptions(beam_size=1, max_length=dims.n_text_ctx), return_trace=True)
     rep = _compare_ids(got, ref, trace)
     print(f"[greedy {which} ts={with_ts}] {rep}")
+    bound = near_tie_bound(which, request.getfixturevalue(which))
     for b, status, margin in rep:
-        assert status == "identical" or (margin is not None and margin < NEAR_TIE), (b, status, margin)
+        assert status == "identical" or (margin is not None and margin < bound), (b, status, margin, bound)
     n_new = dims.n_text_ctx // 2
     assert all(len(g.sequences_ids[0]) <= n_new for g in got)
     if with_ts:
@@ -196,7 +215,7 @@ def test_eot_and_forced_eot_and_long_prompt(small):
     with torch.no_grad():
         ref, trace = generate(emu, enc.float().cpu(), lp, tok, GenOptions(beam_size=1, max_length=dims.n_text_ctx), return_trace=True)
     for b, status, margin in _compare_ids(got, ref, trace):
-        assert status == "identical" or (margin is not None and margin < NEAR_TIE)
+        assert status == "identical" or (margin is not None and margin < near_tie_bound("small", small)), (b, status, margin)
     assert all(len(g.sequences_ids[0]) <= min(dims.n_text_ctx // 2, dims.n_text_ctx - len(lp)) for g in got)
 
 
@@ -238,7 +257,7 @@ def test_long_prompt_batched_prefill_equals_stepwise_oracle(small, beam):
         with torch.no_grad():
             ref, trace = generate(emu, enc.float().cpu(), lp, tok, GenOptions(beam_size=1, max_length=dims.n_text_ctx), return_trace=True)
         for b, status, margin in _compare_ids(got, ref, trace):
-            assert status == "identical" or (margin is not None and margin < NEAR_TIE), (b, status, margin)
+            assert status == "identical" or (margin is not None and margin < near_tie_bound("small", small)), (b, status, margin)
         return
     with torch.no_grad():
         ref = generate(emu, enc.float().cpu(), lp, tok, GenOptions(beam_size=beam, max_length=dims.n_text_ctx))
