@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ = REPO / "build" / ("obj_bf16" if bf16 else "obj")
     LIB = PKG / ("libmw_b200_bf16.so" if bf16 else "libmw_b200.so")
     OBJ.mkdir(parents=True, exist_ok=True)
-    extra = ["-DMW_STORAGE_BF16"] if bf16 else []
+    extra = (["-DMW_STORAGE_BF16"] if bf16 else []) + os.environ.get("MW_EXTRA_NVCC", "").split()
     srcs = sorted(CSRC.glob("*.cu"))
     hdr = max(_newest_header(), Path(__file__).stat().st_mtime)
     jobs = []

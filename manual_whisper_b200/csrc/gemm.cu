@@ -64,8 +64,14 @@ __device__ __forceinline__ float gelu_erf(float v) {
     return 0.5f * v * (1.0f + copysignf(erf_abs, v));
 }
 
+#ifndef MW_GEMM_MINBLOCKS
+#define MW_GEMM_MINBLOCKS 1
+#endif
+#ifndef MW_GEMM_STAGES256
+#define MW_GEMM_STAGES256 4
+#endif
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, MW_GEMM_MINBLOCKS)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const GemmParams p) {
     using L = SmemLayout<BLOCK_N, STAGES>;
@@ -343,7 +349,7 @@ mw_status gemm_launch(const GemmArgs& a, cudaStream_t st) {
     p.bias = a.bias; p.residual = a.residual; p.res_batch_rows = a.res_batch_rows; p.ld_res = a.ld_res;
     p.out = a.out; p.out_batch_rows = a.out_batch_rows; p.out_row_off = a.out_row_off; p.ld_out = a.ld_out;
     p.gelu = a.gelu ? 1 : 0; p.out_f32 = a.out_f32 ? 1 : 0;
-    if (block_n == 256) return launch_cfg<256, 4>(ta, tw, p, st);
+    if (block_n == 256) return launch_cfg<256, MW_GEMM_STAGES256>(ta, tw, p, st);
     return launch_cfg<128, 6>(ta, tw, p, st);
 }
 
