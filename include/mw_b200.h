@@ -199,6 +199,18 @@ mw_status mw_layernorm(const float* d_x, const float* d_gamma, const float* d_be
  * Feeds the energy VAD so the waveform is uploaded once and never revisited by the host. */
 mw_status mw_frame_rms(const float* d_audio, int64_t n, int frame, float* d_out, void* stream);
 
+/* The rest of that front end on the device: frame RMS (as written by mw_frame_rms, frame_s seconds per frame) -> energy
+ * speech score (dB mapped between the 10 % and 95 % points of a 2048-bin histogram) -> Binarize hysteresis (onset / offset,
+ * turns cut at max_duration_s) -> gaps shorter than min_off_s filled, turns shorter than min_on_s dropped ->
+ * Vad.merge_chunks(chunk_size_s).  d_scratch: >= 8192 + 16 * max_turns bytes.  d_windows: double [max_windows][2] =
+ * (start_s, end_s); d_counts: int32 [3] = {turns kept, windows written, overflow flag}.  Replaces the host pass of
+ * whisperx's Binarize + merge_chunks (/root/reference/transcribe.py:43-46,112); manual_whisper_b200/vad.py: EnergyVad is
+ * the host twin with the same float64 arithmetic. */
+mw_status mw_vad_windows(const float* d_rms, int64_t n_frames, double frame_s, double onset, double offset,
+                         double max_duration_s, double min_on_s, double min_off_s, double chunk_size_s,
+                         void* d_scratch, int max_turns, double* d_windows, int max_windows, int32_t* d_counts,
+                         void* stream);
+
 /* Measurement hook for bench.py's roofline: average duration (ms, CUDA events on `stream`) of one hot decode
  * kernel launched `iters` times back to back over different layers' data (inputs larger than L2).
  * which: 0 = cross-attention decode, 1 = skinny GEMM (fc1 weights), 2 = skinny GEMM (out-proj weights). */

@@ -218,9 +218,13 @@ class FasterWhisperPipeline:
             waveform = resident["audio"][self.device].unsqueeze(0)
         else:
             waveform = torch.from_numpy(audio).unsqueeze(0)
-        vad_segments = self.vad_model({"waveform": waveform, "sample_rate": SAMPLE_RATE})
-        vad_segments = merge_chunks(vad_segments, chunk_size, onset=self._vad_params["vad_onset"],
-                                    offset=self._vad_params["vad_offset"])
+        if hasattr(self.vad_model, "device_windows"):
+            # turns AND merge_chunks on the device (csrc/vad.cu): only the finished window table comes back
+            vad_segments = self.vad_model.device_windows({"waveform": waveform, "sample_rate": SAMPLE_RATE}, chunk_size)
+        else:
+            vad_segments = self.vad_model({"waveform": waveform, "sample_rate": SAMPLE_RATE})
+            vad_segments = merge_chunks(vad_segments, chunk_size, onset=self._vad_params["vad_onset"],
+                                        offset=self._vad_params["vad_offset"])
 
         language, task = self._prepare_tokenizer(audio, language, task)
         segments = self.transcribe_windows_host(audio, vad_segments, batch_size=batch_size, language=language, task=task,

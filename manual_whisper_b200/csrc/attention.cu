@@ -151,7 +151,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 const float p0 = ex2(fmaf(__uint_as_float(half ? r1[i] : r0[i]), scale_log2e, -mb));
                 const float p1 = ex2(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), scale_log2e, -mb));
                 if (i & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
-                mw_h2 hh = f2h2(p0, p1);
+                mw_h2 hh = f2h2_bounded(p0, p1);      // p in [0, 1]
                 packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
             }
 #pragma unroll
@@ -206,7 +206,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                mw_h2 hh = f2h2(acc[8 * g + 2 * i] * inv, acc[8 * g + 2 * i + 1] * inv);
+                mw_h2 hh = f2h2_bounded(acc[8 * g + 2 * i] * inv, acc[8 * g + 2 * i + 1] * inv);      // convex combination of V rows
                 w[i] = *reinterpret_cast<uint32_t*>(&hh);
             }
             o4[g] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -26,6 +26,7 @@ __device__ __forceinline__ mw_h f2h(float v) { return __float2bfloat16(v); }
 __device__ __forceinline__ float h2f(mw_h v) { return __bfloat162float(v); }
 __device__ __forceinline__ mw_h2 f2h2(float a, float b) { return __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ float2 h22f2(mw_h2 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ mw_h2 f2h2_bounded(float a, float b) { return __floats2bfloat162_rn(a, b); }
 #else
 typedef __half mw_h;
 typedef __half2 mw_h2;
@@ -39,6 +40,8 @@ __device__ __forceinline__ mw_h2 f2h2(float a, float b) {
     return __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
 }
 __device__ __forceinline__ float2 h22f2(mw_h2 v) { return __half22float2(v); }
+// for values known to lie inside the fp16 range (softmax probabilities, convex combinations of stored values): no clamp
+__device__ __forceinline__ mw_h2 f2h2_bounded(float a, float b) { return __floats2half2_rn(a, b); }
 #endif
 
 namespace mw {

@@ -74,17 +74,31 @@ class InjectedVad:
         return list(self.segments)
 
 
+VAD_BINS, VAD_DB_LO, VAD_DB_HI = 2048, -140.0, 20.0      # csrc/vad.cu
+
+
+def _hist_percentile(hist: np.ndarray, n: int, q: float) -> float:
+    """Lower edge of the histogram bin in which the cumulative count first exceeds q*n (csrc/vad.cu: hist_percentile)."""
+    cum = np.cumsum(hist.astype(np.int64))
+    idx = int(np.searchsorted(cum.astype(np.float64), q * float(n), side="right"))
+    return VAD_DB_HI if idx >= VAD_BINS else VAD_DB_LO + idx * ((VAD_DB_HI - VAD_DB_LO) / VAD_BINS)
+
+
 class EnergyVad:
     """Frame-energy VAD with onset/offset hysteresis and a maximum turn duration — a stand-in for the
     pyannote segmentation + Binarize(onset, offset, max_duration) stage.  NOT numerically related to
-    pyannote; it only provides the same interface so the pipeline is runnable without gated weights."""
+    pyannote; it only provides the same interface so the pipeline is runnable without gated weights.
+
+    Score: dB of the frame RMS mapped to [0, 1] between the 10 % and 95 % points of a 2048-bin histogram over
+    [-140, 20] dB (float64 throughout), which is exactly what csrc/vad.cu computes on the device: this class is the host
+    twin of ``GpuEnergyVad`` and the two produce identical turns and windows."""
 
     def __init__(self, vad_onset: float = 0.5, vad_offset: float = 0.363, chunk_size: float = 30.0,
                  frame_s: float = 0.02, min_duration_on: float = 0.1, min_duration_off: float = 0.1):
         self.onset, self.offset = float(vad_onset), float(vad_offset)
         self.max_duration = float(chunk_size)
         self.frame = int(round(frame_s * SAMPLE_RATE))
-        self.min_on, self.min_off = min_duration_on, min_duration_off
+        self.min_on, self.min_off = float(min_duration_on), float(min_duration_off)
 
     def frame_rms(self, audio: Dict) -> np.ndarray:
         wav = audio["waveform"]
@@ -94,18 +108,18 @@ class EnergyVad:
             return np.zeros(0, np.float32)
         return np.sqrt((wav[: n * self.frame].reshape(n, self.frame) ** 2).mean(axis=1) + 1e-12)
 
-    def __call__(self, audio: Dict) -> List[SegmentX]:
-        e = self.frame_rms(audio)
+    def turns_from_rms(self, e: np.ndarray) -> List[List[float]]:
         n = len(e)
         if n == 0:
             return []
-        db = 20 * np.log10(e)
-        # map energy to a [0, 1] speech score between the noise floor and the loud percentile
-        lo, hi = np.percentile(db, 10), np.percentile(db, 95)
+        db = 20.0 * np.log10(e.astype(np.float64))
+        bins = np.clip(np.floor((db - VAD_DB_LO) * (VAD_BINS / (VAD_DB_HI - VAD_DB_LO))), 0, VAD_BINS - 1).astype(np.int64)
+        hist = np.bincount(bins, minlength=VAD_BINS)
+        lo, hi = _hist_percentile(hist, n, 0.10), _hist_percentile(hist, n, 0.95)
         score = np.clip((db - lo) / max(hi - lo, 6.0), 0.0, 1.0)
         fs = self.frame / SAMPLE_RATE
         turns, active, start = [], False, 0.0
-        for i, s in enumerate(score):
+        for i, s in enumerate(score.tolist()):
             t = i * fs
             if not active and s > self.onset:
                 active, start = True, t
@@ -121,31 +135,65 @@ class EnergyVad:
                 merged[-1][1] = b
             else:
                 merged.append([a, b])
-        return [SegmentX(a, b) for a, b in merged if b - a >= self.min_on]
+        return [[a, b] for a, b in merged if b - a >= self.min_on]
+
+    def __call__(self, audio: Dict) -> List[SegmentX]:
+        return [SegmentX(a, b) for a, b in self.turns_from_rms(self.frame_rms(audio))]
 
 
 class GpuEnergyVad(EnergyVad):
-    """EnergyVad whose per-frame RMS is computed on the GPU (mw_frame_rms).  `wants_device = True` tells the pipeline to
-    upload the waveform ONCE, run the VAD on the device copy and reuse that copy for the ASR batches (SURVEY.md §8f
-    rank 1: the host never revisits the audio); only n/320 floats come back for the hysteresis pass."""
+    """The VAD front end on the GPU: per-frame RMS (mw_frame_rms), energy score, Binarize hysteresis,
+    gap fill and Vad.merge_chunks (mw_vad_windows) all run on the device copy of the waveform.  `wants_device = True` tells
+    the pipeline to upload the waveform ONCE and reuse that copy for the ASR batches; the host never revisits the audio and
+    only the finished tables (turns and windows: a few hundred doubles) come back.  ``device_windows`` is what the pipeline
+    calls; ``__call__`` (turns only, for API parity with other VAD objects) goes through the same kernels."""
     wants_device = True
+    MAX_TURNS, MAX_WINDOWS = 1 << 16, 1 << 14
 
-    def frame_rms(self, audio: Dict) -> np.ndarray:
+    def _run(self, audio: Dict, chunk_size: float):
         import ctypes as C
         import torch
         from . import _lib
+        lib = _lib.load()
         wav = audio["waveform"]
         if not (hasattr(wav, "is_cuda") and wav.is_cuda):
             wav = torch.as_tensor(np.asarray(wav, dtype=np.float32)).cuda()
         wav = wav.reshape(-1).contiguous()
         n = wav.numel() // self.frame
         if n == 0:
-            return np.zeros(0, np.float32)
-        out = torch.empty(n, dtype=torch.float32, device=wav.device)
-        with torch.cuda.device(wav.device):
-            _lib.check(_lib.load().mw_frame_rms(wav.data_ptr(), wav.numel(), self.frame, out.data_ptr(),
-                                                C.c_void_p(torch.cuda.current_stream(wav.device).cuda_stream)), "mw_frame_rms")
-        return out.cpu().numpy()
+            return np.zeros((0, 2)), np.zeros((0, 2))
+        dev = wav.device
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rms = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.check(lib.mw_frame_rms(wav.data_ptr(), wav.numel(), self.frame, rms.data_ptr(), st), "mw_frame_rms")
+            scratch = torch.empty(8192 + 16 * self.MAX_TURNS, dtype=torch.uint8, device=dev)
+            windows = torch.empty((self.MAX_WINDOWS, 2), dtype=torch.float64, device=dev)
+            counts = torch.empty(3, dtype=torch.int32, device=dev)
+            _lib.check(lib.mw_vad_windows(rms.data_ptr(), n, self.frame / SAMPLE_RATE, self.onset, self.offset, self.max_duration,
+                                          self.min_on, self.min_off, float(chunk_size), scratch.data_ptr(), self.MAX_TURNS,
+                                          windows.data_ptr(), self.MAX_WINDOWS, counts.data_ptr(), st), "mw_vad_windows")
+            c = counts.cpu().numpy()
+            if c[2]:
+                raise RuntimeError("mw_vad_windows: more speech turns or windows than the device tables hold")
+            turns = scratch[8192: 8192 + 16 * int(c[0])].view(torch.float64).reshape(-1, 2).cpu().numpy()
+            return turns, windows[: int(c[1])].cpu().numpy()
+
+    def device_windows(self, audio: Dict, chunk_size: float = 30.0) -> List[Dict]:
+        """What merge_chunks(self(audio), chunk_size) returns, computed on the device."""
+        turns, wins = self._run(audio, chunk_size)
+        if len(wins) == 0:
+            print("No active speech found in audio")
+            return []
+        out = []
+        for a, b in wins.tolist():
+            inside = [(float(s), float(e)) for s, e in turns.tolist() if s >= a and e <= b]
+            out.append({"start": float(a), "end": float(b), "segments": inside})
+        return out
+
+    def __call__(self, audio: Dict) -> List[SegmentX]:
+        turns, _ = self._run(audio, self.max_duration)
+        return [SegmentX(float(a), float(b)) for a, b in turns.tolist()]
 
 
 def synthetic_speech(duration_s: float, seed: int = 1, sr: int = SAMPLE_RATE):

@@ -131,8 +131,46 @@ def test_beam_search_on_concurrent_replicas_matches_single_stream(setup):
     assert six.last_stats["replicas"] >= 4
 
 
+def test_device_vad_windows_equal_the_host_twin_exactly():
+    """mw_vad_windows (score, Binarize hysteresis, gap fill, merge_chunks on the device) against the host twin fed with the
+    SAME device frame energies: turns and windows bit-equal, incl. a 1-hour recording, a turn longer than 30 s that must be
+    cut at max_duration, silence, and clips shorter than a frame."""
+    import manual_whisper_b200 as mw
+    from manual_whisper_b200.vad import merge_chunks
+    import ctypes as C
+    from manual_whisper_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    hour, _ = mw.synthetic_speech(3600.0, seed=1)
+    long_turn = (0.1 * rng.standard_normal(16000 * 90)).astype(np.float32)            # 75 s of continuous "speech" ...
+    long_turn[: 16000 * 15] *= 1e-3                                                   # ... after 15 s of background
+    cases = {"hour": hour, "200s": mw.synthetic_speech(200.0, seed=2)[0], "long_turn": long_turn,
+             "silence": np.zeros(16000 * 5, np.float32), "tiny": np.zeros(100, np.float32)}
+    for name, a in cases.items():
+        vad = mw.GpuEnergyVad()
+        d = torch.from_numpy(a).cuda()
+        n = d.numel() // vad.frame
+        rms = torch.empty(max(n, 1), dtype=torch.float32, device="cuda")
+        if n:
+            _lib.check(lib.mw_frame_rms(d.data_ptr(), d.numel(), vad.frame, rms.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rms")
+        want_turns = mw.EnergyVad().turns_from_rms(rms[:n].cpu().numpy())
+        got_turns, got_wins = vad._run({"waveform": d[None], "sample_rate": 16000}, 30.0)
+        assert got_turns.tolist() == want_turns, name
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            want_wins = merge_chunks(want_turns, 30.0)
+        assert got_wins.tolist() == [[w["start"], w["end"]] for w in want_wins], name
+        if name == "hour":
+            assert 100 <= len(got_wins) <= 160 and max(b - a_ for a_, b in got_wins.tolist()) <= 30.0 + 1e-9
+        if name == "long_turn":
+            assert len(got_turns) >= 3 and max(b - a_ for a_, b in got_turns.tolist()) <= 30.0 + 1e-9
+        if name in ("silence", "tiny"):
+            assert len(got_wins) == 0 or name == "silence"
+        print(f"[vad {name}] {len(got_turns)} turns -> {len(got_wins)} windows")
+
+
 def test_device_side_vad_front_end(setup):
-    """frame energies on the GPU give the same turns as the host VAD and the same transcript."""
+    """the VAD front end on the GPU gives the same turns as the host VAD and the same transcript."""
     mw, dims, tok, sd, audio, turns, pipe = setup
     a = audio[: 16000 * 90]
     host = mw.EnergyVad()({"waveform": torch.from_numpy(a)[None], "sample_rate": 16000})
