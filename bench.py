@@ -209,7 +209,9 @@ def run_reference(args):
     total = sum(t)
     v = audio / total
     variants = {}
-    if not args.no_variants:
+    # the driver's scaling run gives every arm 870 s: with K >= 10 full-length steps (~24 s each on 16 cores) the variant rows
+    # (another ~40 s) are left to the default invocation
+    if not args.no_variants and args.steps < 10:
         # the same batch once each with 32 tokens: the reference's default thread count (whisperx threads=4) and plain fp32
         for name, int8, threads in (("int8_all_cores", True, cores), ("int8_threads4", True, 4), ("fp32_all_cores", False, cores)):
             secs, dt, p = ref.step(0, int8=int8, threads=threads, decode_steps=32)
