@@ -5,10 +5,14 @@
 // One CTA = one (batch, head, 128-query tile); 128 threads, thread i owns query row i.
 //   S = Q K_j^T        tcgen05.mma 128x64x64   (Q, K_j: TMA, K-major SWIZZLE_128B)        -> TMEM cols [0,64)
 //   softmax            thread reads its S row (64 fp32) with tcgen05.ld, max / exp2 in registers, writes the
-//                      un-normalised P as bf16 into 128B-swizzled shared memory (A operand of the next MMA)
-//   O_j = P V_j        tcgen05.mma 128x64x64   (V_j: TMA tile [keys, d] used MN-major)      -> TMEM cols [64,128)
-//   acc = acc*alpha + O_j in registers (fp32), final acc / l -> bf16.
-// Four CTAs fit per SM (48 KB smem, 128 TMEM columns each), so one CTA's softmax overlaps the others' MMAs.
+//                      un-normalised P (16-bit) into 128B-swizzled shared memory (A operand of the next MMA)
+//   O += P V_j         tcgen05.mma 128x64x64   (V_j: TMA tile [keys, d] used MN-major)      -> TMEM cols [64,128)
+// Round 2: O is ACCUMULATED IN TMEM across key blocks instead of being read back and rescaled in registers every block
+// (that was 2 tcgen05.ld + 64 FMAs per row per block on an issue-bound kernel).  The exponent reference of a row is only
+// moved - and its O row rescaled through tcgen05.ld/st - when a block's maximum exceeds it by more than 2^8 ("lazy
+// rescale": after the first blocks it practically never happens; P <= 256 fits 16-bit storage with the same relative
+// rounding), and S of block j+1 is issued as soon as every thread has copied S_j to registers, so it runs on the tensor
+// core under the softmax of block j.  K and V are double-buffered.  Three CTAs per SM (64 KB smem, 128 TMEM columns).
 #include "gemm.cuh"
 #include "ptx_sm100.cuh"
 
@@ -23,7 +27,8 @@ constexpr int DH = 64;
 constexpr int Q_BYTES = TQ * DH * 2;       // 16 KB
 constexpr int KV_BYTES = TK * DH * 2;      // 8 KB
 constexpr int P_BYTES = TQ * TK * 2;       // 16 KB: 128 rows x 128 bytes (one swizzle row per query)
-constexpr int ATT_SMEM = Q_BYTES + 2 * KV_BYTES + P_BYTES + 128 + 1024;   // + barriers + alignment slack
+constexpr int ATT_SMEM = Q_BYTES + 4 * KV_BYTES + P_BYTES + 128 + 1024;   // K, V double-buffered; + barriers + alignment slack
+constexpr float RESCALE_LOG2 = 8.0f;       // a row's exponent reference moves only when a block maximum exceeds it by 2^8
 constexpr int ATT_TMEM_COLS = 128;         // S: cols [0,64)   O: cols [64,128)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -32,8 +37,6 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// 4 CTAs per SM (48 KB smem, 128 TMEM columns, <= 128 registers): while one CTA runs its softmax the tensor core
-// serves the others, which is what hides the MMA / mbarrier / tcgen05.ld latencies of the serial per-block chain.
 __global__ void __launch_bounds__(128, 3)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                          mw_h* __restrict__ out, int Tq, int Tk_max, int colq0, int colk0, int colv0, int out_ld,
@@ -41,16 +44,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
-    unsigned char* sK = smem + Q_BYTES;
-    unsigned char* sV = sK + KV_BYTES;
-    unsigned char* sP = sV + KV_BYTES;
+    unsigned char* sK = smem + Q_BYTES;                 // two K buffers
+    unsigned char* sV = sK + 2 * KV_BYTES;              // two V buffers
+    unsigned char* sP = sV + 2 * KV_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* bar_q = bars;
-    uint64_t* bar_k = bars + 1;
-    uint64_t* bar_v = bars + 2;
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_o = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bar_k = bars + 1;       // [2]
+    uint64_t* bar_v = bars + 3;       // [2]
+    uint64_t* bar_s = bars + 5;
+    uint64_t* bar_o = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * TQ;
@@ -65,7 +68,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (tid == 0) {
         prefetch_tensormap(&tmap_q);
         prefetch_tensormap(&tmap_kv);
-        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -81,48 +84,53 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     const uint32_t tmem_o = tmem_base + 64;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_q, Q_BYTES);
-        tma_load_3d(sQ, &tmap_q, bar_q, col_q, q0, b);
-        mbar_arrive_expect_tx(bar_k, KV_BYTES);
-        tma_load_3d(sK, &tmap_kv, bar_k, col_k, 0, b);
-        mbar_arrive_expect_tx(bar_v, KV_BYTES);
-        tma_load_3d(sV, &tmap_kv, bar_v, col_v, 0, b);
-    }
-
     constexpr uint32_t idesc_s = make_idesc_h16(128, TK, 0);
     constexpr uint32_t idesc_o = make_idesc_h16(128, DH, 1);   // B (=V) is MN-major
 
-    float acc[DH];
+    auto issue_s = [&](int j) {        // thread 0: S = Q K_j^T into TMEM cols [0,64)
+        mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dq = make_desc_sw128(smem_u32(sQ), 1024, 0);
+        const uint64_t dk = make_desc_sw128(smem_u32(sK + (j & 1) * KV_BYTES), 1024, 0);
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.0f;
-    float m_run = -INFINITY, l_run = 0.0f;
+        for (int k = 0; k < DH / 16; ++k) umma_h16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(bar_s);
+    };
+
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar_q, Q_BYTES);
+        tma_load_3d(sQ, &tmap_q, bar_q, col_q, q0, b);
+        for (int j = 0; j < 2 && j < n_blocks; ++j) {
+            mbar_arrive_expect_tx(&bar_k[j], KV_BYTES);
+            tma_load_3d(sK + j * KV_BYTES, &tmap_kv, &bar_k[j], col_k, j * TK, b);
+            mbar_arrive_expect_tx(&bar_v[j], KV_BYTES);
+            tma_load_3d(sV + j * KV_BYTES, &tmap_kv, &bar_v[j], col_v, j * TK, b);
+        }
+        mbar_wait(bar_q, 0);
+        issue_s(0);
+    }
+    __syncwarp();
+
+    float m_used = -INFINITY, l_run = 0.0f;       // exponent reference of this row (raw score units), running sum of P
 
     for (int j = 0; j < n_blocks; ++j) {
-        if (tid == 0) {
-            if (j == 0) mbar_wait(bar_q, 0);
-            mbar_wait(bar_k, j & 1);
-            tc_fence_after();
-            const uint64_t dq = make_desc_sw128(smem_u32(sQ), 1024, 0);
-            const uint64_t dk = make_desc_sw128(smem_u32(sK), 1024, 0);
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) umma_h16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-            umma_commit(bar_s);
-        }
-        __syncwarp();
-        mbar_wait(bar_s, j & 1);
+        mbar_wait(bar_s, j & 1);                  // S_j is in TMEM
         tc_fence_after();
-        if (tid == 0 && j + 1 < n_blocks) {      // K buffer is free again: fetch the next block under the softmax
-            mbar_arrive_expect_tx(bar_k, KV_BYTES);
-            tma_load_3d(sK, &tmap_kv, bar_k, col_k, (j + 1) * TK, b);
+        if (tid == 0 && j + 2 < n_blocks) {       // K buffer j&1 is free again
+            mbar_arrive_expect_tx(&bar_k[j & 1], KV_BYTES);
+            tma_load_3d(sK + (j & 1) * KV_BYTES, &tmap_kv, &bar_k[j & 1], col_k, (j + 2) * TK, b);
         }
         __syncwarp();
-        const int n_valid = min(TK, Tk - j * TK);    // >= 1
-        // S row -> registers (64 fp32), max, exp2, bf16 P into the swizzled A-operand tile
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_s + lane_off, r0);
         tmem_ld32(tmem_s + lane_off + 32, r1);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncthreads();                          // every thread holds its S_j row: the S columns may be overwritten
+        if (tid == 0 && j + 1 < n_blocks) issue_s(j + 1);      // runs on the tensor core under this block's softmax
+        __syncwarp();
+
+        const int n_valid = min(TK, Tk - j * TK);    // >= 1
         if (n_valid < TK) {       // last, partial block only: masked keys contribute exp2(-inf) = 0
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -138,78 +146,100 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mx2 = fmaxf(mx2, __uint_as_float(r1[i]));
             mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
         }
-        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-        const float alpha = ex2((m_run - m_new) * scale_log2e);   // m_run = -inf on the first block -> 0
-        const float mb = m_new * scale_log2e;
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // lazy rescale, decided per warp (tcgen05.ld/st are warp-wide): move the exponent reference only when some row of
+        // the warp would otherwise produce P > 2^8
+        const bool need = __any_sync(0xffffffffu, (mx - m_used) * scale_log2e > RESCALE_LOG2);
+        if (need) {
+            const float m_new = fmaxf(m_used, mx);
+            const float alpha = ex2((m_used - m_new) * scale_log2e);       // m_used = -inf on the first block -> 0
+            l_run *= alpha;
+            m_used = m_new;
+            if (j > 0) {
+                mbar_wait(bar_o, (j - 1) & 1);    // O holds blocks 0..j-1
+                tc_fence_after();
+                uint32_t o0[32];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(tmem_o + lane_off + half * 32, o0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+                    tmem_st32(tmem_o + lane_off + half * 32, o0);
+                }
+                tmem_st_wait();
+            }
+        }
+        const float mb = m_used * scale_log2e;
         float ls0 = 0.0f, ls1 = 0.0f, ls2 = 0.0f, ls3 = 0.0f;
-        unsigned char* prow = sP + tid * 128;
+        uint32_t packed[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            uint32_t packed[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
                 const float p0 = ex2(fmaf(__uint_as_float(half ? r1[i] : r0[i]), scale_log2e, -mb));
                 const float p1 = ex2(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), scale_log2e, -mb));
                 if (i & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
-                mw_h2 hh = f2h2_bounded(p0, p1);      // p in [0, 1]
-                packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int chunk = (half * 4 + g) ^ (tid & 7);
-                *reinterpret_cast<uint4*>(prow + chunk * 16) =
-                    make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                mw_h2 hh = f2h2_bounded(p0, p1);      // p <= 2^8
+                packed[half * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
             }
         }
-        const float lsum = (ls0 + ls1) + (ls2 + ls3);
-        l_run = l_run * alpha + lsum;
-        m_run = m_new;
+        l_run += (ls0 + ls1) + (ls2 + ls3);
+        if (j > 0) {
+            mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} has read sP and V buffer (j-1)&1 (long done by now)
+            if (tid == 0 && j + 1 < n_blocks) {
+                mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], KV_BYTES);
+                tma_load_3d(sV + ((j + 1) & 1) * KV_BYTES, &tmap_kv, &bar_v[(j + 1) & 1], col_v, (j + 1) * TK, b);
+            }
+            __syncwarp();
+        }
+        unsigned char* prow = sP + tid * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int chunk = g ^ (tid & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+        }
         fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
-        __syncthreads();          // P complete, every S read retired
+        __syncthreads();          // P complete, rescaled O rows stored
         if (tid == 0) {
-            mbar_wait(bar_v, j & 1);
+            mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TK / 16; ++k) {
                 const uint64_t dp = make_desc_sw128(smem_u32(sP) + k * 32, 1024, 0);
-                const uint64_t dv = make_desc_sw128(smem_u32(sV) + k * 2048, 1024, KV_BYTES);
-                umma_h16(tmem_o, dp, dv, idesc_o, k ? 1u : 0u);
+                const uint64_t dv = make_desc_sw128(smem_u32(sV + (j & 1) * KV_BYTES) + k * 2048, 1024, KV_BYTES);
+                umma_h16(tmem_o, dp, dv, idesc_o, (j | k) ? 1u : 0u);
             }
             umma_commit(bar_o);
         }
         __syncwarp();
-        mbar_wait(bar_o, j & 1);
-        tc_fence_after();
-        if (tid == 0 && j + 1 < n_blocks) {      // V buffer is free again
-            mbar_arrive_expect_tx(bar_v, KV_BYTES);
-            tma_load_3d(sV, &tmap_kv, bar_v, col_v, (j + 1) * TK, b);
-        }
-        __syncwarp();
+    }
+
+    mbar_wait(bar_o, (n_blocks - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + tid;
+    {
+        uint32_t r0[32], r1[32];
         tmem_ld32(tmem_o + lane_off, r0);
         tmem_ld32(tmem_o + lane_off + 32, r1);
         tmem_ld_wait();
+        if (q < Tq) {
+            const float inv = 1.0f / l_run;
+            uint4* o4 = reinterpret_cast<uint4*>(out + ((int64_t)b * Tq + q) * out_ld + h * DH);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            acc[i] = fmaf(acc[i], alpha, __uint_as_float(r0[i]));
-            acc[32 + i] = fmaf(acc[32 + i], alpha, __uint_as_float(r1[i]));
-        }
-        tc_fence_before();
-    }
-
-    const int q = q0 + tid;
-    if (q < Tq) {
-        const float inv = 1.0f / l_run;
-        uint4* o4 = reinterpret_cast<uint4*>(out + ((int64_t)b * Tq + q) * out_ld + h * DH);
+            for (int g = 0; g < 8; ++g) {
+                uint32_t w[4];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                mw_h2 hh = f2h2_bounded(acc[8 * g + 2 * i] * inv, acc[8 * g + 2 * i + 1] * inv);      // convex combination of V rows
-                w[i] = *reinterpret_cast<uint32_t*>(&hh);
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 8 * g + 2 * i;
+                    const float a0 = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]) * inv;
+                    const float a1 = __uint_as_float(c + 1 < 32 ? r0[c + 1] : r1[c + 1 - 32]) * inv;
+                    mw_h2 hh = f2h2_bounded(a0, a1);      // convex combination of V rows
+                    w[i] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                o4[g] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            o4[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
     tc_fence_before();

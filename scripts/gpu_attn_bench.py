@@ -3,7 +3,7 @@ sys.path.insert(0, ".")
 from manual_whisper_b200 import _lib
 lib = _lib.load(); dev = torch.device("cuda:0")
 B, T, H = 32, 1500, 20; d = H * 64
-qkv = torch.randn(B * T, 3 * d, device=dev).bfloat16(); out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+H16 = _lib.storage_dtype(); qkv = torch.randn(B * T, 3 * d, device=dev).to(H16); out = torch.empty(B * T, d, device=dev, dtype=H16)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(3): lib.mw_attention_h16(qkv.data_ptr(), out.data_ptr(), B, T, H, st)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
