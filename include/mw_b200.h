@@ -236,6 +236,10 @@ typedef struct mw_w2v_config {
     int32_t max_batch;       /* windows per mw_w2v_emissions call */
     int32_t max_samples;     /* longest window in samples (480000 = 30 s) */
     int32_t device;
+    int32_t variant;         /* 0: feat_extract_norm="layer", do_stable_layer_norm=True (XLSR-53 family: the reference's zh model);
+                              * 1: wav2vec2-base (what whisperx loads for en/fr/de/es/it): GroupNorm after conv0 only, no conv
+                              *    biases, post-LayerNorm encoder; d_model / pos_groups may then be 48 (pos-conv weight rows padded
+                              *    to 64 per group by the host) */
 } mw_w2v_config;
 
 /* Weight table: MW_A_* globals, then n_layers blocks in the order of enum mw_enc_layer_weight_id (q|k|v rows
@@ -267,6 +271,11 @@ int32_t mw_w2v_frames(int64_t n_samples);
 mw_status mw_w2v_emissions(mw_w2v* model, const float* d_audio, int64_t n_audio, const int64_t* d_offsets,
                            const int32_t* d_lengths, const int32_t* h_lengths, int n, float* d_out,
                            int64_t out_window_stride, void* stream);
+
+/* Test hook: copies one internal buffer of the last mw_w2v_emissions call to d_dst (device): 0 = conv stack output f32
+ * [n*T, conv_dim], 1 = residual stream f32 [n*T, d_model], 2 = GroupNorm statistics f32 [n, conv_dim, 2] (variant 1),
+ * 3 = conv0 output h16 [n, T_0, conv_dim]. */
+mw_status mw_w2v_debug_copy(mw_w2v* model, int which, void* d_dst, int64_t nbytes, void* stream);
 
 /* CTC forced alignment of n windows (whisperx get_trellis + backtrack).  Emissions as written by mw_w2v_emissions;
  * d_frames[c] = valid frames; d_tokens [n, max_tokens] dictionary ids (-1 = wildcard: best non-blank symbol),

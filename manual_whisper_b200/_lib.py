@@ -39,7 +39,7 @@ class ModelConfigC(C.Structure):
 class W2vConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_layers", "d_model", "n_heads", "ffn", "vocab", "conv_dim", "pos_kernel", "pos_groups", "max_batch", "max_samples",
-        "device")]
+        "device", "variant")]
 
 
 class WeightTableC(C.Structure):
@@ -87,6 +87,7 @@ SIGNATURES = {
     "mw_w2v_frames": (C.c_int32, [C.c_int64]),
     "mw_w2v_emissions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_i32p, C.c_int, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
+    "mw_w2v_debug_copy": (C.c_int32, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "mw_pcm_resample": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "mw_ctc_align": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,

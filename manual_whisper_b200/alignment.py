@@ -48,7 +48,10 @@ _N_GLOBAL = 38      # enum mw_w2v_weight_id: MW_A_GLOBAL_COUNT
 
 def pack_w2v_weights(sd: Dict[str, torch.Tensor], dims: W2vDims, device: torch.device) -> List[torch.Tensor]:
     """Hugging Face ``Wav2Vec2ForCTC`` state dict -> the engine's weight table (order of enum mw_w2v_weight_id, then the
-    per-layer blocks of enum mw_enc_layer_weight_id)."""
+    per-layer blocks of enum mw_enc_layer_weight_id).  wav2vec2-base checkpoints (no conv biases, GroupNorm after conv0 only)
+    fill the slots the variant does not read with zeros / ones; positional-conv groups narrower than 64 channels get their
+    weight rows padded to 64 per group."""
+    zeros_c, ones_c = torch.zeros(dims.conv_dim), torch.ones(dims.conv_dim)
     def mat(t):
         return t.to(device=device, dtype=_lib.storage_dtype()).contiguous()
 
@@ -63,12 +66,15 @@ def pack_w2v_weights(sd: Dict[str, torch.Tensor], dims: W2vDims, device: torch.d
             out.append(vec(w[:, 0, :]))                                            # f32 [C, 10]
         else:
             out.append(mat(w.permute(0, 2, 1).reshape(w.shape[0], -1)))             # [co][tap][ci]
-        out += [vec(sd[f"{fe}{i}.conv.bias"]), vec(sd[f"{fe}{i}.layer_norm.weight"]), vec(sd[f"{fe}{i}.layer_norm.bias"])]
+        out += [vec(sd.get(f"{fe}{i}.conv.bias", zeros_c)), vec(sd.get(f"{fe}{i}.layer_norm.weight", ones_c)),
+                vec(sd.get(f"{fe}{i}.layer_norm.bias", zeros_c))]
     fp = "wav2vec2.feature_projection."
     out += [vec(sd[fp + "layer_norm.weight"]), vec(sd[fp + "layer_norm.bias"]), mat(sd[fp + "projection.weight"]),
             vec(sd[fp + "projection.bias"])]
     G, gs, kp = dims.pos_groups, dims.d_model // dims.pos_groups, dims.pos_kernel
     wp = effective_pos_conv_weight(sd).view(G, gs, gs, kp).permute(0, 1, 3, 2)      # [g][out][tap][in]
+    if gs != 64:                                                                    # 64 (zero-padded) output rows per group
+        wp = torch.cat([wp, torch.zeros(G, 64 - gs, kp, gs)], dim=1)
     out += [mat(wp), vec(sd["wav2vec2.encoder.pos_conv_embed.conv.bias"])]
     out += [vec(sd["wav2vec2.encoder.layer_norm.weight"]), vec(sd["wav2vec2.encoder.layer_norm.bias"])]
     vp = (dims.vocab + 31) // 32 * 32
@@ -97,9 +103,13 @@ class AlignEngine:
 
     def __init__(self, dims: W2vDims, sd: Dict[str, torch.Tensor], device_index: int = 0, max_batch: int = 16,
                  max_samples: int = 30 * SAMPLE_RATE):
-        if dims.feat_norm != "layer" or not dims.stable_layer_norm or not dims.conv_bias:
-            raise NotImplementedError("the CUDA alignment engine implements the layer-norm / stable-layer-norm wav2vec2 family "
-                                      "(XLSR-53); the group-norm wav2vec2-base variant is not built yet")
+        xlsr = dims.feat_norm == "layer" and dims.stable_layer_norm and dims.conv_bias
+        base = dims.feat_norm == "group" and not dims.stable_layer_norm and not dims.conv_bias
+        if not (xlsr or base):
+            raise NotImplementedError("the CUDA alignment engine implements the two wav2vec2 families whisperx loads: layer-norm / "
+                                      "stable-layer-norm / conv-bias (XLSR-53) and group-norm / post-layer-norm / no conv bias "
+                                      f"(wav2vec2-base); got feat_norm={dims.feat_norm!r} stable_layer_norm={dims.stable_layer_norm} "
+                                      f"conv_bias={dims.conv_bias}")
         if not torch.cuda.is_available():
             raise RuntimeError("manual_whisper_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -108,7 +118,7 @@ class AlignEngine:
         self.max_batch, self.max_samples = int(max_batch), int(max_samples)
         self.weights = pack_w2v_weights(sd, dims, self.device)
         cfg = _lib.W2vConfigC(dims.n_layers, dims.d_model, dims.n_heads, dims.ffn, dims.vocab, dims.conv_dim, dims.pos_kernel,
-                              dims.pos_groups, self.max_batch, self.max_samples, device_index)
+                              dims.pos_groups, self.max_batch, self.max_samples, device_index, 0 if xlsr else 1)
         ptrs = (C.c_void_p * len(self.weights))(*[w.data_ptr() for w in self.weights])
         table = _lib.WeightTableC(len(self.weights), ptrs)
         handle = C.c_void_p()
@@ -204,7 +214,7 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
         from safetensors.torch import load_file
         sd = load_file(ckpt)
         if "lm_head.weight" not in sd or "wav2vec2.feature_extractor.conv_layers.0.layer_norm.weight" not in sd:
-            raise ValueError(f"{ckpt} is not a Hugging Face Wav2Vec2ForCTC checkpoint of the layer-norm (XLSR) family")
+            raise ValueError(f"{ckpt} is not a Hugging Face Wav2Vec2ForCTC checkpoint")
     else:
         sd = None
     if dims is None:

@@ -9,11 +9,13 @@ namespace {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
-// one warp per row; d % 128 == 0, d <= 128 * MAXV.  MODE 0: LN -> bf16; 1: GELU(LN) -> bf16; 2: GELU(LN) -> f32
+// one warp per row; d % 128 == 0, d <= 128 * MAXV.  MODE 0: LN -> h16; 1: GELU(LN) -> h16; 2: GELU(LN) -> f32;
+// 3: LN -> h16 AND f32 written back over x (post-LayerNorm encoders: the normalised row is both the next GEMM operand and
+// the residual stream)
 template <int MAXV, int MODE = 0>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 void* __restrict__ out_v, int rows, int d) {
+layernorm_kernel(const float* x /* MODE 3 writes it back: no __restrict__ */, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, void* out_v, int rows, int d) {
     mw_h* out = reinterpret_cast<mw_h*>(out_v);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -50,11 +52,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
             const float4 g = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
             float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
             float y2 = (v[i].z - mean) * rstd * g.z + bb.z, y3 = (v[i].w - mean) * rstd * g.w + bb.w;
-            if (MODE != 0) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3); }
+            if (MODE == 1 || MODE == 2) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3); }
             if (MODE == 2) {
                 reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + (int64_t)row * d)[i * 32 + lane] = make_float4(y0, y1, y2, y3);
                 continue;
             }
+            if (MODE == 3)      // the row is held in registers: writing it back in place is safe
+                reinterpret_cast<float4*>(const_cast<float*>(x) + (int64_t)row * d)[i * 32 + lane] = make_float4(y0, y1, y2, y3);
             mw_h2 h0 = f2h2(y0, y1);
             mw_h2 h1 = f2h2(y2, y3);
             uint2 u;
@@ -116,6 +120,19 @@ mw_status layernorm_launch(const float* x, const float* gamma, const float* beta
     if (d <= 512) layernorm_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
     else if (d <= 1280) layernorm_kernel<10><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
     else layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, out_bf16, rows, d);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+mw_status layernorm_dual_launch(float* x_inout, const float* gamma, const float* beta, void* out_h16, int rows, int d,
+                                cudaStream_t st) {
+    MW_REQUIRE(x_inout && gamma && beta && out_h16, "layernorm_dual: null pointer");
+    MW_REQUIRE(d % 128 == 0 && d >= 128 && d <= 2048, "layernorm_dual: d=%d must be a multiple of 128 in [128, 2048]", d);
+    if (rows <= 0) return MW_OK;
+    const int grid = ceil_div(rows, 8);
+    if (d <= 512) layernorm_kernel<4, 3><<<grid, 256, 0, st>>>(x_inout, gamma, beta, out_h16, rows, d);
+    else if (d <= 1280) layernorm_kernel<10, 3><<<grid, 256, 0, st>>>(x_inout, gamma, beta, out_h16, rows, d);
+    else layernorm_kernel<16, 3><<<grid, 256, 0, st>>>(x_inout, gamma, beta, out_h16, rows, d);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

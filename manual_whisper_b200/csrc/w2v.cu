@@ -15,8 +15,17 @@
 //   LN -> lm_head GEMM -> log_softmax                                              -> f32 [n, T_n, vocab]
 // Every op before the positional conv is local in time (valid convs, per-frame norms), so padding a window to S samples
 // leaves its first frames(len) frames untouched; the positional conv and attention are told each window's length.
+//
+// variant 1 = wav2vec2-base (what whisperx loads for en/fr/de/es/it; modeling_wav2vec2.py:302-323, 592-609, 658-727):
+//   conv0 has no bias and is followed by GroupNorm(C groups) - per-channel statistics over the window's OWN frames, the one
+//     op that is global in time: a statistics pass over conv0 (deterministic two-level sum), then conv0 is recomputed,
+//     normalised and GELU'd; conv 1..6: GEMM with GELU in the epilogue, no bias, no norm
+//   positional conv groups of 48 channels (768 / 16): weight rows padded to 64 per group, result added by a small kernel
+//   post-LayerNorm encoder: LN right after the positional conv, then per layer x = LN(x + attn(x)); x = LN(x + ffn(x)); no
+//     final LN - LayerNorm writes the fp32 residual stream and the 16-bit GEMM operand at once (layernorm_dual_launch)
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -39,6 +48,10 @@ struct mw_w2v {
     mw_h* mlp = nullptr;         // [B*T, ffn]
     float* logits = nullptr;              // [B*T, vocab_pad]
     int* d_frames = nullptr;              // [B] valid frames per window of the current call
+    // variant 1 (wav2vec2-base)
+    float* gn_partial = nullptr;          // [B, ceil(T_0 / 64), C, 2] per-CTA sums of conv0 and conv0^2
+    float* gn_stats = nullptr;            // [B, C, 2] mean, rstd
+    float* pos_tmp = nullptr;             // [B*T, G*64] positional conv output before bias / GELU / residual
 
     const void* gw(int id) const { return w[id]; }
     const void* lw(int layer, int id) const { return w[MW_A_GLOBAL_COUNT + layer * MW_EL_COUNT + id]; }
@@ -129,19 +142,127 @@ w2v_conv0_kernel(const float* __restrict__ audio, int64_t n_audio, const int64_t
     }
 }
 
-// x f32 [n, T, d] -> bf16 [n, G, T + kp, 64]: row t' holds frame t' - kp/2, zero outside the window's valid frames
+// ---- wav2vec2-base: conv0 (no bias) + GroupNorm(C groups) + GELU.  MODE 0: per-CTA partial sums of conv0 and conv0^2 over
+// the window's own frames; MODE 1: conv0 recomputed, (v - mean_c) rstd_c gamma_c + beta_c, GELU -> h16 time-major.
+template <int NP, int MODE>
+__global__ void __launch_bounds__(256)
+w2v_conv0_gn_kernel(const float* __restrict__ audio, int64_t n_audio, const int64_t* __restrict__ offs, const int* __restrict__ lens,
+                    const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ partial, const float* __restrict__ stats, mw_h* __restrict__ out, int T0, int n_blk) {
+    constexpr int C = 64 * NP;
+    __shared__ float sw[10][C];
+    __shared__ float red[4][2 * C];         // MODE 0: sums of warp pairs (w, w+4); MODE 1: red[0] = scale | shift per channel
+    for (int i = threadIdx.x; i < 10 * C; i += 256) sw[i % 10][i / 10] = w[i];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MODE == 1) {
+        for (int c = threadIdx.x; c < C; c += 256) {
+            const float mean = stats[((int64_t)b * C + c) * 2], rstd = stats[((int64_t)b * C + c) * 2 + 1];
+            red[0][c] = rstd * gamma[c];                       // scale
+            red[0][C + c] = beta[c] - mean * rstd * gamma[c];  // shift
+        }
+    }
+    __syncthreads();
+    const int64_t off = offs[b];
+    const int len = lens[b];
+    const int T0b = conv_frames(max(len, 400), 1);             // this window's own frames (shorter windows are zero-padded to 400)
+    const float* a = audio + off;
+    float ps[NP][2], pq[NP][2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { ps[p][0] = ps[p][1] = pq[p][0] = pq[p][1] = 0.0f; }
+    for (int it = 0; it < 8; ++it) {
+        const int t = blockIdx.x * 64 + it * 8 + warp;
+        if (t >= T0) break;                                  // warp-uniform
+        float xs = 0.0f;
+        if (lane < 10) {
+            const int i = 5 * t + lane;
+            if (i < len && off + i < n_audio) xs = a[i];
+        }
+        float xk[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xk[k] = __shfl_sync(0xffffffffu, xs, k);
+        mw_h* o = out + ((int64_t)b * T0 + t) * C;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int c = 2 * lane + 64 * p;
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const float2 wk = *reinterpret_cast<const float2*>(&sw[k][c]);
+                a0 = fmaf(wk.x, xk[k], a0);
+                a1 = fmaf(wk.y, xk[k], a1);
+            }
+            if (MODE == 0) {
+                if (t < T0b) { ps[p][0] += a0; ps[p][1] += a1; pq[p][0] = fmaf(a0, a0, pq[p][0]); pq[p][1] = fmaf(a1, a1, pq[p][1]); }
+            } else {
+                const float y0 = t < T0b ? gelu_exact(fmaf(a0, red[0][c], red[0][C + c])) : 0.0f;
+                const float y1 = t < T0b ? gelu_exact(fmaf(a1, red[0][c + 1], red[0][C + c + 1])) : 0.0f;
+                *reinterpret_cast<mw_h2*>(o + c) = f2h2(y0, y1);
+            }
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {             // warps 4..7 park their sums, warps 0..3 fold them in
+            if ((warp >= 4) == (round == 0)) {
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int c = 2 * lane + 64 * p;
+                    float* r = red[warp & 3];
+                    if (round == 1) { ps[p][0] += r[c]; ps[p][1] += r[c + 1]; pq[p][0] += r[C + c]; pq[p][1] += r[C + c + 1]; }
+                    r[c] = ps[p][0]; r[c + 1] = ps[p][1];
+                    r[C + c] = pq[p][0]; r[C + c + 1] = pq[p][1];
+                }
+            }
+            __syncthreads();
+        }
+        float* dst = partial + ((int64_t)b * n_blk + blockIdx.x) * 2 * C;
+        for (int i = threadIdx.x; i < 2 * C; i += 256)
+            dst[i] = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);       // fixed order
+    }
+}
+
+// per (window, channel): mean and rstd from the per-CTA partial sums, summed in block order in double (deterministic)
+__global__ void w2v_gn_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ lens, float* __restrict__ stats,
+                                       int C, int n_blk) {
+    const int b = blockIdx.x;
+    const int T0b = conv_frames(max(lens[b], 400), 1);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        const float* p = partial + (int64_t)b * n_blk * 2 * C;
+        for (int k = 0; k < n_blk; ++k) { s += p[(int64_t)k * 2 * C + c]; q += p[(int64_t)k * 2 * C + C + c]; }
+        const double mean = s / (double)T0b;
+        const double var = fmax(q / (double)T0b - mean * mean, 0.0);
+        stats[((int64_t)b * C + c) * 2] = (float)mean;
+        stats[((int64_t)b * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+}
+
+// x f32 [n, T, d] -> h16 [n, G, T + kp, gw] (gw = d / G channels per group): row t' holds frame t' - kp/2, zero outside the
+// window's valid frames
 __global__ void __launch_bounds__(256)
 w2v_group_major_kernel(const float* __restrict__ x, const int* __restrict__ frames, mw_h* __restrict__ xg, int T, int d,
-                       int kp) {
+                       int kp, int gw) {
     const int tp = blockIdx.x, b = blockIdx.y;
     const int t = tp - kp / 2;
     const bool valid = t >= 0 && t < min(frames[b], T);
-    const int G = d >> 6;
+    const int G = d / gw;
     const float* src = x + ((int64_t)b * T + t) * d;
     for (int c = threadIdx.x; c < d; c += 256) {
-        const int g = c >> 6, ci = c & 63;
-        xg[(((int64_t)b * G + g) * (T + kp) + tp) * 64 + ci] = f2h(valid ? src[c] : 0.0f);
+        const int g = c / gw, ci = c - g * gw;
+        xg[(((int64_t)b * G + g) * (T + kp) + tp) * gw + ci] = f2h(valid ? src[c] : 0.0f);
     }
+}
+
+// groups narrower than 64 channels: x[r, g*gw + c] += GELU(tmp[r, g*64 + c] + bias[g*gw + c])
+__global__ void __launch_bounds__(256)
+w2v_pos_add_kernel(const float* __restrict__ tmp, const float* __restrict__ bias, float* __restrict__ x, int64_t rows, int d, int gw) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows * d) return;
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d), g = c / gw, ci = c - g * gw;
+    const int G = d / gw;
+    x[i] += gelu_exact(tmp[r * (int64_t)(G * 64) + g * 64 + ci] + bias[c]);
 }
 
 // logits f32 [n*T, ldl] -> log_softmax over the first V columns, written to the caller's [frames_c, V] block of window c
@@ -281,7 +402,13 @@ extern "C" mw_status mw_w2v_create(const mw_w2v_config* cfg, const mw_weight_tab
     MW_REQUIRE(cfg->d_model == cfg->n_heads * 64, "mw_w2v_create: d_head must be 64 (d_model=%d n_heads=%d)", cfg->d_model, cfg->n_heads);
     MW_REQUIRE(cfg->d_model % 128 == 0 && cfg->ffn % 128 == 0, "mw_w2v_create: d_model and ffn must be multiples of 128");
     MW_REQUIRE(cfg->conv_dim == 128 || cfg->conv_dim == 256 || cfg->conv_dim == 512, "mw_w2v_create: conv_dim must be 128, 256 or 512");
-    MW_REQUIRE(cfg->pos_groups > 0 && cfg->d_model == cfg->pos_groups * 64, "mw_w2v_create: d_model / pos_groups must be 64");
+    MW_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "mw_w2v_create: variant must be 0 (XLSR family) or 1 (wav2vec2-base)");
+    MW_REQUIRE(cfg->pos_groups > 0 && cfg->d_model % cfg->pos_groups == 0, "mw_w2v_create: d_model must be a multiple of pos_groups");
+    {
+        const int gw = cfg->d_model / cfg->pos_groups;
+        MW_REQUIRE(gw == 64 || (cfg->variant == 1 && gw % 8 == 0 && gw < 64 && (cfg->pos_kernel * gw) % 64 == 0),
+                   "mw_w2v_create: d_model / pos_groups = %d is not supported (64; or a multiple of 8 below 64 for variant 1)", gw);
+    }
     MW_REQUIRE(cfg->pos_kernel >= 2 && cfg->pos_kernel % 2 == 0, "mw_w2v_create: pos_kernel must be even");
     MW_REQUIRE(cfg->max_batch > 0 && cfg->max_samples >= 400 && cfg->vocab > 1 && cfg->n_layers > 0, "mw_w2v_create: bad sizes");
     const int expect = MW_A_GLOBAL_COUNT + cfg->n_layers * MW_EL_COUNT;
@@ -308,6 +435,11 @@ extern "C" mw_status mw_w2v_create(const mw_w2v_config* cfg, const mw_weight_tab
     A((void**)&m->mlp, B * T * cfg->ffn * 2);
     A((void**)&m->logits, B * T * m->vocab_pad * 4);
     A((void**)&m->d_frames, B * 4);
+    if (cfg->variant == 1) {
+        A((void**)&m->gn_partial, B * ((m->T_max[0] + 63) / 64) * 2 * C * 4);
+        A((void**)&m->gn_stats, B * C * 2 * 4);
+        if (d / cfg->pos_groups != 64) A((void**)&m->pos_tmp, B * T * cfg->pos_groups * 64 * 4);
+    }
     if (s != MW_OK) { mw_w2v_destroy(m); return s; }
     *out_model = m;
     return MW_OK;
@@ -344,7 +476,25 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
     mw_status s;
     w2v_frames_kernel<<<ceil_div(n, 128), 128, 0, st>>>(d_lengths, n, m->d_frames);
     MW_LAUNCH_CHECK();
-    {
+    const bool base = c.variant == 1;
+    if (base) {
+        const int n_blk = ceil_div(Tl[0], 64);
+        dim3 grid(n_blk, n);
+        const float* w0 = (const float*)m->gw(MW_A_CONV0_W);
+        const float* g0 = (const float*)m->gw(MW_A_CONV0_LN_G);
+        const float* be0 = (const float*)m->gw(MW_A_CONV0_LN_B);
+#define MW_GN(np)                                                                                                              \
+        w2v_conv0_gn_kernel<np, 0><<<grid, 256, 0, st>>>(d_audio, n_audio, d_offsets, d_lengths, w0, g0, be0, m->gn_partial,    \
+                                                         nullptr, m->act_a, Tl[0], n_blk);                                      \
+        MW_LAUNCH_CHECK();                                                                                                      \
+        w2v_gn_finalize_kernel<<<n, 256, 0, st>>>(m->gn_partial, d_lengths, m->gn_stats, C, n_blk);                             \
+        MW_LAUNCH_CHECK();                                                                                                      \
+        w2v_conv0_gn_kernel<np, 1><<<grid, 256, 0, st>>>(d_audio, n_audio, d_offsets, d_lengths, w0, g0, be0, nullptr,          \
+                                                         m->gn_stats, m->act_a, Tl[0], n_blk);                                  \
+        MW_LAUNCH_CHECK();
+        if (C == 512) { MW_GN(8) } else if (C == 256) { MW_GN(4) } else { MW_GN(2) }
+#undef MW_GN
+    } else {
         dim3 grid(ceil_div(Tl[0], 64), n);
         const float* w0 = (const float*)m->gw(MW_A_CONV0_W);
         const float* b0 = (const float*)m->gw(MW_A_CONV0_B);
@@ -360,11 +510,18 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
         GemmArgs a;
         a.a = in; a.a_row_stride = (int64_t)CONV_S[l] * C; a.a_batch_stride = (int64_t)Tl[l - 1] * C;
         a.w = m->gw(MW_A_CONV0_W + 4 * l); a.w_row_stride = (int64_t)CONV_K[l] * C;
+        void* out = l == 6 ? (void*)m->feat : (void*)((l & 1) ? m->act_b : m->act_a);
+        if (base) {      // conv (no bias) + GELU in the GEMM epilogue, no norm; the last layer stays fp32 (it feeds a LayerNorm)
+            a.out = out; a.out_batch_rows = Tl[l]; a.ld_out = C;
+            a.batch = n; a.M = Tl[l]; a.N = C; a.K = CONV_K[l] * C; a.gelu = true; a.out_f32 = l == 6;
+            if ((s = gemm_launch(a, st)) != MW_OK) return s;
+            in = (const mw_h*)out;
+            continue;
+        }
         a.bias = (const float*)m->gw(MW_A_CONV0_W + 4 * l + 1);
         a.out = m->conv_f32; a.out_batch_rows = Tl[l]; a.ld_out = C;
         a.batch = n; a.M = Tl[l]; a.N = C; a.K = CONV_K[l] * C; a.out_f32 = true;
         if ((s = gemm_launch(a, st)) != MW_OK) return s;
-        void* out = l == 6 ? (void*)m->feat : (void*)((l & 1) ? m->act_b : m->act_a);
         if ((s = layernorm_act_launch(m->conv_f32, (const float*)m->gw(MW_A_CONV0_W + 4 * l + 2),
                                       (const float*)m->gw(MW_A_CONV0_W + 4 * l + 3), out, n * Tl[l], C, l == 6 ? 2 : 1, st)) != MW_OK)
             return s;
@@ -380,22 +537,35 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
         if ((s = gemm_launch(a, st)) != MW_OK) return s;
     }
     {   // x += GELU(pos_conv(x) + bias): one implicit GEMM per 64-channel group over the group-major copy
-        const int kp = c.pos_kernel, G = c.pos_groups;
-        w2v_group_major_kernel<<<dim3(T + kp, n), 256, 0, st>>>(m->x, m->d_frames, m->xg, T, d, kp);
+        const int kp = c.pos_kernel, G = c.pos_groups, gw = d / G;
+        w2v_group_major_kernel<<<dim3(T + kp, n), 256, 0, st>>>(m->x, m->d_frames, m->xg, T, d, kp, gw);
         MW_LAUNCH_CHECK();
         for (int g = 0; g < G; ++g) {
             GemmArgs a;
-            a.a = m->xg + (int64_t)g * (T + kp) * 64; a.a_row_stride = 64; a.a_batch_stride = (int64_t)G * (T + kp) * 64;
-            a.w = (const mw_h*)m->gw(MW_A_POS_W) + (int64_t)g * 64 * kp * 64; a.w_row_stride = (int64_t)kp * 64;
-            a.bias = (const float*)m->gw(MW_A_POS_B) + g * 64;
-            a.residual = m->x + g * 64; a.res_batch_rows = T; a.ld_res = d;
-            a.out = m->x + g * 64; a.out_batch_rows = T; a.ld_out = d;
-            a.batch = n; a.M = T; a.N = 64; a.K = kp * 64; a.gelu = true; a.out_f32 = true;
+            a.a = m->xg + (int64_t)g * (T + kp) * gw; a.a_row_stride = gw; a.a_batch_stride = (int64_t)G * (T + kp) * gw;
+            a.w = (const mw_h*)m->gw(MW_A_POS_W) + (int64_t)g * 64 * kp * gw; a.w_row_stride = (int64_t)kp * gw;
+            a.batch = n; a.M = T; a.N = 64; a.K = kp * gw; a.out_f32 = true;
+            if (gw == 64) {
+                a.bias = (const float*)m->gw(MW_A_POS_B) + g * 64;
+                a.residual = m->x + g * 64; a.res_batch_rows = T; a.ld_res = d;
+                a.out = m->x + g * 64; a.out_batch_rows = T; a.ld_out = d;
+                a.gelu = true;
+            } else {     // narrower groups: 64 padded output columns per group into a scratch buffer, added below
+                a.out = m->pos_tmp + g * 64; a.out_batch_rows = T; a.ld_out = (int64_t)G * 64;
+            }
             if ((s = gemm_launch(a, st)) != MW_OK) return s;
         }
+        if (gw != 64) {
+            const int64_t tot = (int64_t)rows * d;
+            w2v_pos_add_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(m->pos_tmp, (const float*)m->gw(MW_A_POS_B), m->x, rows, d, gw);
+            MW_LAUNCH_CHECK();
+        }
     }
+    { const char* e = getenv("MW_W2V_STOP"); if (e && e[0] == 'p') return MW_OK; }      // debug: x = projection + pos conv
+    if (base)      // post-LayerNorm encoder: the encoder LayerNorm comes right after the positional embedding
+        if ((s = layernorm_dual_launch(m->x, (const float*)m->gw(MW_A_ENC_LN_G), (const float*)m->gw(MW_A_ENC_LN_B), m->ln, rows, d, st)) != MW_OK) return s;
     for (int l = 0; l < c.n_layers; ++l) {
-        if ((s = layernorm_launch(m->x, (const float*)m->lw(l, MW_EL_LN1_G), (const float*)m->lw(l, MW_EL_LN1_B), m->ln, rows, d, st)) != MW_OK) return s;
+        if (!base && (s = layernorm_launch(m->x, (const float*)m->lw(l, MW_EL_LN1_G), (const float*)m->lw(l, MW_EL_LN1_B), m->ln, rows, d, st)) != MW_OK) return s;
         {
             GemmArgs a;
             a.a = m->ln; a.a_row_stride = d; a.w = m->lw(l, MW_EL_WQKV); a.w_row_stride = d;
@@ -412,7 +582,9 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
             a.out = m->x; a.ld_out = d; a.M = rows; a.N = d; a.K = d; a.out_f32 = true;
             if ((s = gemm_launch(a, st)) != MW_OK) return s;
         }
-        if ((s = layernorm_launch(m->x, (const float*)m->lw(l, MW_EL_LN2_G), (const float*)m->lw(l, MW_EL_LN2_B), m->ln, rows, d, st)) != MW_OK) return s;
+        if (base) {      // x = LN(x + attn(x)): written back as the residual stream and as the fc1 operand
+            if ((s = layernorm_dual_launch(m->x, (const float*)m->lw(l, MW_EL_LN1_G), (const float*)m->lw(l, MW_EL_LN1_B), m->ln, rows, d, st)) != MW_OK) return s;
+        } else if ((s = layernorm_launch(m->x, (const float*)m->lw(l, MW_EL_LN2_G), (const float*)m->lw(l, MW_EL_LN2_B), m->ln, rows, d, st)) != MW_OK) return s;
         {
             GemmArgs a;
             a.a = m->ln; a.a_row_stride = d; a.w = m->lw(l, MW_EL_W1); a.w_row_stride = d;
@@ -428,8 +600,9 @@ extern "C" mw_status mw_w2v_emissions(mw_w2v* m, const float* d_audio, int64_t n
             a.out = m->x; a.ld_out = d; a.M = rows; a.N = d; a.K = c.ffn; a.out_f32 = true;
             if ((s = gemm_launch(a, st)) != MW_OK) return s;
         }
+        if (base && (s = layernorm_dual_launch(m->x, (const float*)m->lw(l, MW_EL_LN2_G), (const float*)m->lw(l, MW_EL_LN2_B), m->ln, rows, d, st)) != MW_OK) return s;
     }
-    if ((s = layernorm_launch(m->x, (const float*)m->gw(MW_A_ENC_LN_G), (const float*)m->gw(MW_A_ENC_LN_B), m->ln, rows, d, st)) != MW_OK) return s;
+    if (!base && (s = layernorm_launch(m->x, (const float*)m->gw(MW_A_ENC_LN_G), (const float*)m->gw(MW_A_ENC_LN_B), m->ln, rows, d, st)) != MW_OK) return s;
     {
         GemmArgs a;
         a.a = m->ln; a.a_row_stride = d; a.w = m->gw(MW_A_LM_W); a.w_row_stride = d;
@@ -460,5 +633,17 @@ extern "C" mw_status mw_ctc_align(const float* d_emissions, int64_t window_strid
                                                                      d_n_tokens, blank, d_workspace, wild, max_frames, d_frame_token,
                                                                      d_frame_score, d_ok);
     MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+// test hook: copy one of the model's internal buffers of the last mw_w2v_emissions call to the caller (device to device).
+// which: 0 = conv stack output feat f32 [n*T, C], 1 = residual stream x f32 [n*T, d], 2 = GroupNorm statistics f32 [n, C, 2],
+// 3 = conv0 output h16 [n, T_0, C]
+extern "C" mw_status mw_w2v_debug_copy(mw_w2v* m, int which, void* d_dst, int64_t nbytes, void* stream) {
+    MW_REQUIRE(m && d_dst && nbytes > 0, "mw_w2v_debug_copy: bad argument");
+    const void* src = which == 0 ? (const void*)m->feat : which == 1 ? (const void*)m->x : which == 2 ? (const void*)m->gn_stats
+                                                                                         : (const void*)m->act_a;
+    MW_REQUIRE(src != nullptr, "mw_w2v_debug_copy: buffer %d is not allocated for this variant", which);
+    MW_CUDA_CHECK(cudaMemcpyAsync(d_dst, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return MW_OK;
 }

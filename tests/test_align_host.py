@@ -161,8 +161,26 @@ def test_align_control_flow_on_cpu_with_an_oracle_engine(capsys):
     assert out[0]["start"] == w0["start"] and out[0]["end"] == out[0]["words"][-1]["end"]
 
 
-def test_engine_rejects_the_group_norm_variant_loudly():
+def test_engine_accepts_both_whisperx_families_and_rejects_hybrids():
+    """XLSR (layer norm, stable LN, conv bias) and wav2vec2-base (group norm, post-LN, no conv bias) are built; anything in
+    between is refused before any device work."""
     from dataclasses import replace
-    base = replace(W2vDims(), feat_norm="group", stable_layer_norm=False, conv_bias=False)
-    with pytest.raises(NotImplementedError, match="group-norm"):
-        AL.AlignEngine(base, {}, device_index=0)
+    hybrid = replace(W2vDims(), feat_norm="group", stable_layer_norm=True, conv_bias=False)
+    with pytest.raises(NotImplementedError, match="two wav2vec2 families"):
+        AL.AlignEngine(hybrid, {}, device_index=0)
+
+
+def test_pack_base_variant_pads_missing_slots_and_narrow_pos_groups():
+    from dataclasses import replace
+    dims = replace(W2vDims(name="b", n_layers=1, d_model=384, n_heads=6, ffn=256, vocab=40, conv_dim=128, pos_kernel=8, pos_groups=8),
+                   feat_norm="group", stable_layer_norm=False, conv_bias=False)
+    sd = random_init_w2v(dims, seed=0)
+    assert "wav2vec2.feature_extractor.conv_layers.0.conv.bias" not in sd
+    assert "wav2vec2.feature_extractor.conv_layers.1.layer_norm.weight" not in sd
+    packed = AL.pack_w2v_weights(sd, dims, torch.device("cpu"))
+    assert len(packed) == 38 + 12
+    assert torch.all(packed[1] == 0) and torch.all(packed[5] == 0)               # absent conv biases
+    assert torch.all(packed[6] == 1) and torch.all(packed[7] == 0)               # conv 1 has no norm in this variant
+    assert packed[32].shape == (8, 64, 8, 48) and torch.all(packed[32][:, 48:] == 0)     # 48-channel groups, rows padded to 64
+    wp = effective_pos_conv_weight(sd)
+    assert torch.equal(packed[32].float()[3, 5, 2, 9], wp[3 * 48 + 5, 9, 2])

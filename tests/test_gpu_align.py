@@ -57,6 +57,48 @@ def test_emissions_match_oracle_on_ragged_batch(small):
         assert torch.all(em[c, T:] == 0)                                             # rows beyond the window stay untouched
 
 
+BASE_SMALL = None
+
+
+def _base_dims(**kw):
+    from dataclasses import replace
+    return replace(W2vDims(**kw), feat_norm="group", stable_layer_norm=False, conv_bias=False)
+
+
+@pytest.mark.parametrize("which", ["small48", "base768"])
+def test_wav2vec2_base_variant_matches_oracle(which):
+    """wav2vec2-base family (what whisperx loads for en/fr/de/es/it): GroupNorm after conv0 over each window's OWN frames, no
+    conv biases, 48-channel positional-conv groups, post-LayerNorm encoder.  Oracle pinned to transformers' Wav2Vec2ForCTC
+    (tests/test_oracle_align.py); ragged batch incl. a window shorter than 400 samples; a window in a batch equals its solo run."""
+    from manual_whisper_b200.alignment import AlignEngine
+    if which == "small48":
+        dims = _base_dims(name="w2v-base-test", n_layers=2, d_model=384, n_heads=6, ffn=512, vocab=40, conv_dim=128, pos_kernel=16, pos_groups=8)
+        lens = np.array([16000, 5003, 40000, 250], dtype=np.int32)
+    else:       # facebook/wav2vec2-base-960h: 12 layers, d 768, 12 heads, ffn 3072, 16 positional groups of 48 channels
+        dims = _base_dims(name="w2v-base", n_layers=12, d_model=768, n_heads=12, ffn=3072, vocab=32, conv_dim=512, pos_kernel=128, pos_groups=16)
+        lens = np.array([24000, 9001], dtype=np.int32)
+    sd = random_init_w2v(dims, seed=13)
+    eng = AlignEngine(dims, sd, device_index=0, max_batch=4, max_samples=40000)
+    audio = _audio(70000, 3)
+    offs = np.array([0, 16000, 30000, 69000][: len(lens)], dtype=np.int64)
+    em, frames = eng.emissions(torch.from_numpy(audio).cuda(), offs, lens)
+    em = em.cpu()
+    for c in range(len(lens)):
+        T = int(frames[c])
+        wave = audio[offs[c]: offs[c] + lens[c]]
+        ref = _oracle_emissions(dims, sd, wave, emulate=True)
+        f32 = _oracle_emissions(dims, sd, wave, emulate=False)
+        assert ref.shape == (T, dims.vocab)
+        got = em[c, :T]
+        assert torch.allclose(got.exp().sum(-1), torch.ones(T), atol=1e-4)
+        spread = (f32.max() - f32.min()).item()
+        assert (got - ref).abs().max().item() <= 0.02 * spread, (which, c, (got - ref).abs().max().item(), spread)
+        assert (got - f32).abs().max().item() <= 0.05 * spread
+    solo, f1 = eng.emissions(torch.from_numpy(audio).cuda(), offs[1:2], lens[1:2])
+    assert int(f1[0]) == int(frames[1])
+    assert (solo[0, : int(f1[0])].cpu() - em[1, : int(frames[1])]).abs().max().item() < 1e-4      # GroupNorm statistics are per window
+
+
 def test_batched_window_equals_solo_run(small):
     sd, eng = small
     audio = _audio(60000, 1)
