@@ -29,7 +29,8 @@ import torch
 
 from . import _lib
 from .config import SAMPLE_RATE
-from .w2v import W2vDims, random_init_w2v, effective_pos_conv_weight
+from .w2v import (W2vDims, random_init_w2v, effective_pos_conv_weight, torchaudio_to_hf, is_torchaudio_state_dict, base_dims,
+                  BASE_LANGUAGES)
 
 LANGUAGES_WITHOUT_SPACES = ["ja", "zh"]
 WILDCARD = -1
@@ -209,7 +210,7 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
     if dictionary is None:
         dictionary = dict(DEFAULT_DICTIONARY)
     if isinstance(model, dict):
-        sd = model
+        sd = torchaudio_to_hf(model) if is_torchaudio_state_dict(model) else model      # torchaudio bundles: whisperx's en/fr/de/es/it
     elif ckpt is not None:
         from safetensors.torch import load_file
         sd = load_file(ckpt)
@@ -229,6 +230,9 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
                            stable_layer_norm=layer_norm_family, conv_bias=fe + "0.conv.bias" in sd)
         elif DEFAULT_ALIGN_DIMS is not None:
             dims = DEFAULT_ALIGN_DIMS
+        elif language_code in BASE_LANGUAGES:
+            # whisperx's DEFAULT_ALIGN_MODELS_TORCH: the torchaudio wav2vec2-base bundles (group-norm, post-LayerNorm family)
+            dims = base_dims(vocab=max(dictionary.values()) + 1)
         else:
             dims = W2vDims(vocab=max(dictionary.values()) + 1)
     if sd is None:

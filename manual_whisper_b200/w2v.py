@@ -1,9 +1,10 @@
 """wav2vec2-CTC alignment model: dimensions, Hugging Face checkpoint key names and seeded random-init weights.
 
 The reference aligns with ``whisperx.load_align_model(language_code, device)`` (/root/reference/transcribe.py:127-129); for
-"zh" that is a Hugging Face ``Wav2Vec2ForCTC`` of the XLSR-53 family (feat_extract_norm="layer", do_stable_layer_norm=True),
-which is the variant the CUDA engine implements (csrc/w2v.cu).  No checkpoint exists offline, so `random_init_w2v` provides
-seeded weights of that architecture for tests and benchmarks.
+"zh" that is a Hugging Face ``Wav2Vec2ForCTC`` of the XLSR-53 family (feat_extract_norm="layer", do_stable_layer_norm=True);
+for en/fr/de/es/it whisperx loads torchaudio's wav2vec2-base bundles (group-norm extractor, post-LayerNorm encoder).  The CUDA
+engine implements both families (csrc/w2v.cu, variant 0 / 1).  No checkpoint exists offline, so `random_init_w2v` provides
+seeded weights of either architecture for tests and benchmarks; `torchaudio_to_hf` renames a torchaudio state dict.
 """
 from __future__ import annotations
 
@@ -26,8 +27,8 @@ class W2vDims:
     conv_stride: Tuple[int, ...] = (5, 2, 2, 2, 2, 2, 2)
     pos_kernel: int = 128
     pos_groups: int = 16
-    # "layer" + stable_layer_norm=True is the XLSR-53 family (what the CUDA engine implements); "group" + False + no conv
-    # bias is wav2vec2-base (whisperx's torchaudio models for en/fr/de/es/it) - oracle only so far
+    # "layer" + stable_layer_norm=True + conv bias is the XLSR-53 family; "group" + False + no conv bias is wav2vec2-base
+    # (whisperx's torchaudio models for en/fr/de/es/it); the CUDA engine implements exactly these two combinations
     feat_norm: str = "layer"
     stable_layer_norm: bool = True
     conv_bias: bool = True
@@ -52,6 +53,40 @@ def effective_pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         g, v = sd[p + "weight_g"], sd[p + "weight_v"]
     g, v = g.float().cpu(), v.float().cpu()
     return v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))
+
+
+def torchaudio_to_hf(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """State dict of a ``torchaudio.models.Wav2Vec2Model`` (what whisperx's English / French / German / Spanish / Italian
+    alignment models are: ``torchaudio.pipelines.WAV2VEC2_ASR_BASE_960H.get_model()`` etc.) -> the Hugging Face
+    ``Wav2Vec2ForCTC`` key names the rest of this package uses.  Same tensors, renamed: the two implementations share the
+    architecture (tests/test_oracle_align.py pins the mapping against torchaudio's forward pass)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.startswith("feature_extractor."):
+            nk = "wav2vec2." + k
+        elif k.startswith("encoder.feature_projection."):
+            nk = "wav2vec2." + k[len("encoder."):]
+        elif k.startswith("encoder.transformer."):
+            nk = "wav2vec2.encoder." + k[len("encoder.transformer."):]
+        elif k.startswith("aux."):
+            nk = "lm_head." + k[len("aux."):]
+        else:
+            raise ValueError(f"unexpected torchaudio wav2vec2 key {k!r}")
+        out[nk] = v
+    return out
+
+
+def is_torchaudio_state_dict(sd) -> bool:
+    return any(k.startswith("encoder.transformer.") for k in sd) and not any(k.startswith("wav2vec2.") for k in sd)
+
+
+# wav2vec2-base: facebook/wav2vec2-base-960h = torchaudio WAV2VEC2_ASR_BASE_960H, the family whisperx aligns en/fr/de/es/it with
+BASE_LANGUAGES = ("en", "fr", "de", "es", "it")
+
+
+def base_dims(vocab: int = 32, name: str = "w2v-base") -> "W2vDims":
+    return W2vDims(name=name, n_layers=12, d_model=768, n_heads=12, ffn=3072, vocab=vocab, conv_dim=512, pos_kernel=128,
+                   pos_groups=16, feat_norm="group", stable_layer_norm=False, conv_bias=False)
 
 
 def random_init_w2v(dims: W2vDims, seed: int = 0, std: float = 0.05) -> Dict[str, torch.Tensor]:

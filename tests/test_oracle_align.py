@@ -63,7 +63,8 @@ def test_wav2vec2_oracle_matches_hf():
 
 
 def test_group_norm_base_variant_oracle_matches_hf():
-    """wav2vec2-base layout (GroupNorm on conv 0, no conv bias, post-LN encoder): oracle only, pinned for the next round."""
+    """wav2vec2-base layout (GroupNorm on conv 0, no conv bias, post-LN encoder), the oracle of tests/test_gpu_align.py's
+    base-variant test, pinned to transformers' Wav2Vec2ForCTC."""
     from dataclasses import replace
     base = replace(SMALL, name="w2v-base-test", feat_norm="group", stable_layer_norm=False, conv_bias=False)
     sd = random_init_w2v(base, seed=4)
@@ -72,6 +73,32 @@ def test_group_norm_base_variant_oracle_matches_hf():
     wave = torch.randn(5000, generator=torch.Generator().manual_seed(1)) * 0.1
     with torch.no_grad():
         want, got = hf(wave[None]).logits[0], ora.logits(wave)
+    assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
+
+
+def test_torchaudio_state_dict_maps_onto_the_oracle():
+    """whisperx aligns en/fr/de/es/it with torchaudio bundles (WAV2VEC2_ASR_BASE_960H ...): a torchaudio Wav2Vec2Model state
+    dict renamed by torchaudio_to_hf gives torchaudio's own logits through the oracle (group-norm / post-LN family)."""
+    import torchaudio
+    from dataclasses import replace
+    from manual_whisper_b200.w2v import torchaudio_to_hf, is_torchaudio_state_dict
+    torch.manual_seed(5)
+    m = torchaudio.models.wav2vec2_model(
+        extractor_mode="group_norm", extractor_conv_layer_config=[(64, 10, 5)] + [(64, 3, 2)] * 4 + [(64, 2, 2)] * 2,
+        extractor_conv_bias=False, encoder_embed_dim=128, encoder_projection_dropout=0.0, encoder_pos_conv_kernel=16,
+        encoder_pos_conv_groups=4, encoder_num_layers=2, encoder_num_heads=2, encoder_attention_dropout=0.0,
+        encoder_ff_interm_features=256, encoder_ff_interm_dropout=0.0, encoder_dropout=0.0, encoder_layer_norm_first=False,
+        encoder_layer_drop=0.0, aux_num_out=40).eval()
+    sd = m.state_dict()
+    assert is_torchaudio_state_dict(sd)
+    hf_sd = torchaudio_to_hf(sd)
+    assert not is_torchaudio_state_dict(hf_sd) and "lm_head.weight" in hf_sd
+    dims = replace(SMALL, name="ta", feat_norm="group", stable_layer_norm=False, conv_bias=False)
+    wave = torch.randn(6000, generator=torch.Generator().manual_seed(2)) * 0.1
+    with torch.no_grad():
+        want = m(wave[None])[0][0]
+        got = OracleWav2Vec2(dims, hf_sd).logits(wave)
+    assert got.shape == want.shape
     assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
 
 
