@@ -142,6 +142,10 @@ class OracleWhisper:
         mask = None
         if n > 1:
             mask = torch.full((n, pos0 + n), float("-inf")).triu(pos0 + 1)
+        grouped = False
+        if cross_index is not None and cross[0][0].shape[0] > 0 and R % cross[0][0].shape[0] == 0:
+            Bc = cross[0][0].shape[0]
+            grouped = bool(torch.equal(cross_index, torch.arange(Bc).repeat_interleave(R // Bc)))
         for i in range(self.dims.dec_layers):
             p = f"model.decoder.layers.{i}."
             h = _r(self._ln(x, p + "self_attn_layer_norm"), emu)
@@ -157,9 +161,17 @@ class OracleWhisper:
             h = _r(self._ln(x, p + "encoder_attn_layer_norm"), emu)
             q = self._heads(_r(self._lin(h, p + "encoder_attn.q_proj"), emu))
             ck, cv = cross[i]
-            if cross_index is not None:
-                ck, cv = ck[cross_index], cv[cross_index]
-            a = _r(self._attn(q, ck, cv), emu)
+            if cross_index is not None and grouped:
+                # beams of one chunk are consecutive rows: attend as [B, H, k*n, 64] against the chunk's K/V instead of
+                # copying K/V per beam (same dot products; it only spares the oracle gigabytes of copies per step)
+                Bc, kb = ck.shape[0], R // ck.shape[0]
+                qg = q.reshape(Bc, kb, q.shape[1], n, q.shape[3]).permute(0, 2, 1, 3, 4).reshape(Bc, q.shape[1], kb * n, q.shape[3])
+                a = self._attn(qg, ck, cv).reshape(Bc, kb, n, -1).reshape(R, n, -1)
+                a = _r(a, emu)
+            else:
+                if cross_index is not None:
+                    ck, cv = ck[cross_index], cv[cross_index]
+                a = _r(self._attn(q, ck, cv), emu)
             x = x + self._lin(a, p + "encoder_attn.out_proj")
             h = _r(self._ln(x, p + "final_layer_norm"), emu)
             h = _r(F.gelu(self._lin(h, p + "fc1")), emu)
