@@ -16,9 +16,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _fixture(model):
+def _fixture(model, tag=""):
     from scripts.make_parity_fixture import fixture_path
-    path = fixture_path(model, "peaked")
+    path = fixture_path(model, "peaked", tag)
     if not os.path.exists(path):
         pytest.skip(f"{path} has not been generated")
     fx = np.load(path)
@@ -61,5 +61,29 @@ def test_large_v3_config2_one_chunk_and_a_batch():
     assert np.array_equal(got[0], got1[0])                                  # batch of 1 == the same window inside a batch of 32
     for tag, ref in (("large-v3 vs rounding oracle", fx["ids_emu"][:n]), ("large-v3 vs fp32 oracle", fx["ids_fp32"][:n])):
         cmp = compare(got, ref, margins[:n])
+        _report(tag, cmp)
+        assert cmp["fraction"] >= 0.99, cmp["divergences"]
+
+
+def test_small_config4_beam5_with_timestamp_rules():
+    """BASELINE config 4: Whisper small (80 mels), beam_size 5, patience 1, length_penalty 1, without_timestamps=False (the
+    timestamp logit rules run on the device), batch_size 16 - hypothesis 0 of every window against the oracle's beam search on
+    the same weights, plus the structure the rules guarantee."""
+    from scripts.gpu_parity_stats import engine_ids, compare
+    from manual_whisper_b200.config import special_tokens
+    fx, meta = _fixture("small", "_beam5_ts")
+    assert meta["beam"] == 5 and meta["with_timestamps"]
+    n = meta["windows"]
+    got, offs, lens, _ = engine_ids(meta, n, batch=16)
+    assert np.array_equal(offs, fx["offs"]) and np.array_equal(lens, fx["lens"])
+    tok = special_tokens(51865)
+    for row in got:
+        ids = row[row >= 0]
+        assert len(ids) >= 1 and tok.timestamp_begin <= ids[0] <= tok.timestamp_begin + 50          # max_initial_timestamp_index
+        ts = ids[ids >= tok.timestamp_begin]
+        assert np.all(np.diff(ts) >= 0)                                                             # timestamps never decrease
+    margins = np.full(got.shape, np.nan, dtype=np.float32)
+    for tag, ref in (("small beam5 vs rounding oracle", fx["ids_emu"]), ("small beam5 vs fp32 oracle", fx["ids_fp32"])):
+        cmp = compare(got, ref, margins)
         _report(tag, cmp)
         assert cmp["fraction"] >= 0.99, cmp["divergences"]
