@@ -185,6 +185,12 @@ mw_status mw_attention_h16(const void* d_qkv, void* d_out, int B, int T, int n_h
  * X,W h16; out h16, or f32 when flags&2; R <= 256, K % 64 == 0.  W is streamed once for all R rows. */
 mw_status mw_decode_gemm_h16(const void* d_x, const void* d_w, const float* d_bias, const float* d_residual,
                              void* d_out, int R, int N, int K, int flags, void* stream);
+/* Scheduling hint for mw_generate: solo != 0 says this model (replica) is the only one decoding on its GPU, so the step is
+ * built for latency (LayerNorm folded into the projections that consume it: 96 fewer launches per large-v3 step, -4 % per step);
+ * solo == 0 (default) is the form that is faster when several replicas decode concurrently.  Same ids either way.  The host
+ * mirror sets it per job (asr.py run_device_batches: one batch in flight -> solo), e.g. one recording sharded over 8 GPUs
+ * (/root/reference/transcribe.py:123 with device_index=[0..7]). */
+mw_status mw_set_solo(mw_model* model, int solo);
 /* Measurement hook (bench.py "in_step"): keep only the kernel classes in `parts` (the mask of mw_bench_step, plus 64 = token
  * selection) in decode-step graphs captured from now on, process-wide; 127 restores the real step.  Ids are meaningless while a
  * class is missing; the change in step time is that class's cost inside the real, concurrent step. */

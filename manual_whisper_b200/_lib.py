@@ -74,6 +74,7 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_void_p]),
     "mw_decode_gemm_debug": (None, [C.c_void_p]),
     "mw_debug_step_parts": (None, [C.c_int]),
+    "mw_set_solo": (C.c_int32, [C.c_void_p, C.c_int]),
     "mw_attention_h16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mw_bench_kernel": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "mw_bench_step": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),

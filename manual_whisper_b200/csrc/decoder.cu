@@ -84,7 +84,8 @@ struct DecoderState {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // step graphs are specific to (rows, beam): a small cache keeps the last few shapes (full batches and the short
     // last batch of a recording alternate) so they are not re-captured on every call
-    struct Graphs { int R = 0, beam = 0; uint64_t last_use = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
+    bool solo = false;                   // mw_set_solo: this replica decodes alone on its GPU (latency mode, see skinny_gemm_ln)
+    struct Graphs { int R = 0, beam = 0; bool solo = false; uint64_t last_use = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
     static constexpr int GRAPH_CACHE = 4;
     Graphs graph_cache[GRAPH_CACHE];
     uint64_t graph_clock = 0;
@@ -116,11 +117,24 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     return r;
 }
 
+// Weight prefetch: a decode step is a serial chain of short kernels whose weights arrive cold from HBM (one DRAM round trip
+// per launch with nothing else in flight).  Every projection kernel therefore asks L2 for the NEXT projection's weight
+// matrix once its own weights have arrived (`pf`, `pf_lines` 128-byte lines, spread over the grid's threads), so the next
+// kernel's stream starts from L2; the cross-attention kernel does the same for its output projection.
+__device__ __forceinline__ void l2_prefetch_slice(const char* pf, int pf_lines) {
+    if (!pf) return;
+    const int nthr = gridDim.x * gridDim.y * blockDim.x;
+    for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < pf_lines; i += nthr)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (int64_t)i * 128));
+}
+
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                    const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                    int flags) {
     __shared__ float red[8][32][17];
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int n0 = blockIdx.x * 16, r0 = blockIdx.y * 32;
@@ -182,10 +196,11 @@ template <int KB, int NW, int WT>
 __global__ void __launch_bounds__(NW * 32, WT == 2 ? 2 : 1)
 skinny_gemm_rows16_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                           const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
-                          int flags) {
+                          int flags, const char* pf, int pf_lines) {
     // WT = 16-row weight tiles per CTA.  Every CTA re-reads the whole X block [32, K] from L2, so with one tile the L2->SM
     // traffic is 3x the HBM traffic and caps several batches in flight at ~3.3 TB/s of weights; two tiles halve the X share.
     __shared__ float red[NW][32][WT * 16 + 1];
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int n0 = blockIdx.x * (16 * WT), r0 = blockIdx.y * 32;
@@ -201,6 +216,7 @@ skinny_gemm_rows16_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __res
             ahi[wt][i] = ldg_stream(wb + i * 32);
         }
     }
+    pdl_wait();        // the weights above are in flight; X (and resid, out) belong to the chain
     const mw_h* xr[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xr[t] = X + (int64_t)min(r0 + t * 8 + g, R - 1) * ldx + k_start;
@@ -224,6 +240,7 @@ skinny_gemm_rows16_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __res
                 mma_h16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
             }
     }
+    l2_prefetch_slice(pf, pf_lines);
 #pragma unroll
     for (int wt = 0; wt < WT; ++wt)
 #pragma unroll
@@ -251,16 +268,156 @@ skinny_gemm_rows16_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __res
     }
 }
 
+// LayerNorm folded into the projection that consumes it (QKV, cross-attention Q, fc1).  A decode step is a serial chain of
+// ~350 graph nodes and a node costs >= 3.3 us however little it does (scripts/gpu_chain_floor.py), so the 96 stand-alone
+// LayerNorm launches of a large-v3 step were 0.7 ms of a 3.9 ms single-stream step.  Here every CTA normalises its 32 rows
+// itself - warp per row, the SAME lane mapping, summation order and rounding as layernorm_kernel (elementwise.cu), so the
+// 16-bit operand is bit-identical to the stand-alone kernel's - into shared memory, and the MMAs read it from there.
+// The price is L2 traffic (each CTA reads the fp32 rows instead of the 16-bit copy), not HBM traffic.
+template <int KB, int NW, int WT>
+__global__ void __launch_bounds__(NW * 32, WT == 2 ? 2 : 1)
+skinny_gemm_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const mw_h* __restrict__ W, int ldw, const float* __restrict__ bias, mw_h* __restrict__ out, int ldo,
+                      int R, int N, int flags, const char* pf, int pf_lines) {
+    constexpr int K = KB * NW * 32, MAXV = K / 128, XS = K + 32;      // row pitch K + 32: conflict-free 16-byte fragment reads
+    static_assert(K % 128 == 0, "LayerNorm rows are walked in 128-element steps");
+    extern __shared__ __align__(16) unsigned char ln_smem[];
+    mw_h* xs = reinterpret_cast<mw_h*>(ln_smem);                                        // [32][XS]
+    float (*red)[32][WT * 16 + 1] = reinterpret_cast<float (*)[32][WT * 16 + 1]>(ln_smem);   // aliased once the MMAs are done
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int n0 = blockIdx.x * (16 * WT), r0 = blockIdx.y * 32;
+    // ---- LayerNorm of rows r0 .. r0+31, two rows per warp at a time (their loads are in flight together)
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    for (int rl0 = warp; rl0 < 32; rl0 += 2 * NW) {
+        float4 v[2][MAXV];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)min(r0 + rl0 + h * NW, R - 1) * K);
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) v[h][i] = xr[i * 32 + lane];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int rl = rl0 + h * NW;
+            if (rl >= 32) break;
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) s += (v[h][i].x + v[h][i].y) + (v[h][i].z + v[h][i].w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s / (float)K;
+            float qq = 0.0f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const float a = v[h][i].x - mean, b = v[h][i].y - mean, c = v[h][i].z - mean, e = v[h][i].w - mean;
+                qq += (a * a + b * b) + (c * c + e * e);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+            const float rstd = rsqrtf(qq / (float)K + 1e-5f);
+            uint2* o2 = reinterpret_cast<uint2*>(xs + rl * XS);
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+                const float y0 = (v[h][i].x - mean) * rstd * gg.x + bb.x, y1 = (v[h][i].y - mean) * rstd * gg.y + bb.y;
+                const float y2 = (v[h][i].z - mean) * rstd * gg.z + bb.z, y3 = (v[h][i].w - mean) * rstd * gg.w + bb.w;
+                mw_h2 h0 = f2h2(y0, y1);
+                mw_h2 h1 = f2h2(y2, y3);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                o2[i * 32 + lane] = u;
+            }
+        }
+    }
+    // ---- the projection, as skinny_gemm_rows16_kernel with the X fragments read from shared memory
+    const int k_start = warp * (KB * 32) + q * 8;
+    uint4 alo[WT][KB], ahi[WT][KB];
+#pragma unroll
+    for (int wt = 0; wt < WT; ++wt) {
+        const mw_h* wa = W + (int64_t)min(n0 + wt * 16 + g, N - 1) * ldw + k_start;
+        const mw_h* wb = W + (int64_t)min(n0 + wt * 16 + g + 8, N - 1) * ldw + k_start;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+            alo[wt][i] = ldg_stream(wa + i * 32);
+            ahi[wt][i] = ldg_stream(wb + i * 32);
+        }
+    }
+    __syncthreads();
+    float c[WT][4][4];
+#pragma unroll
+    for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[wt][t][i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+        uint4 b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) b[t] = *reinterpret_cast<const uint4*>(xs + (t * 8 + g) * XS + k_start + i * 32);
+#pragma unroll
+        for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                mma_h16_16816(c[wt][t], alo[wt][i].x, ahi[wt][i].x, alo[wt][i].y, ahi[wt][i].y, b[t].x, b[t].y);
+                mma_h16_16816(c[wt][t], alo[wt][i].z, ahi[wt][i].z, alo[wt][i].w, ahi[wt][i].w, b[t].z, b[t].w);
+            }
+    }
+    l2_prefetch_slice(pf, pf_lines);
+    __syncthreads();          // every warp has read its X fragments: the reduction buffer may overwrite them
+#pragma unroll
+    for (int wt = 0; wt < WT; ++wt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            red[warp][t * 8 + 2 * q][wt * 16 + g] = c[wt][t][0];
+            red[warp][t * 8 + 2 * q + 1][wt * 16 + g] = c[wt][t][1];
+            red[warp][t * 8 + 2 * q][wt * 16 + g + 8] = c[wt][t][2];
+            red[warp][t * 8 + 2 * q + 1][wt * 16 + g + 8] = c[wt][t][3];
+        }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 32 * 16 * WT; o += NW * 32) {
+        const int rl = o / (16 * WT), nl = o % (16 * WT);
+        const int r = r0 + rl, n = n0 + nl;
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += red[w][rl][nl];
+        if (r < R && n < N) {
+            if (bias) v += __ldg(bias + n);
+            if (flags & SK_FLAG_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+            out[(int64_t)r * ldo + n] = f2h(v);
+        }
+    }
+}
+
+template <int KB, int NW>
+mw_status launch_ln_rows16(const float* x, const float* gamma, const float* beta, const void* W, int ldw, const float* bias,
+                           void* out, int ldo, int R, int N, int flags, cudaStream_t st, const char* pf, int pf_lines) {
+    constexpr int WT = 2, K = KB * NW * 32;
+    constexpr int xs_bytes = 32 * (K + 32) * 2, red_bytes = NW * 32 * (WT * 16 + 1) * 4;
+    constexpr int smem = xs_bytes > red_bytes ? xs_bytes : red_bytes;
+    static PerDeviceOnce attr_once;
+    MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(skinny_gemm_ln_kernel<KB, NW, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
+    dim3 grid(ceil_div(N, 16 * WT), ceil_div(R, 32));
+    skinny_gemm_ln_kernel<KB, NW, WT><<<grid, NW * 32, smem, st>>>(x, gamma, beta, (const mw_h*)W, ldw, bias, (mw_h*)out, ldo, R, N,
+                                                                  flags, pf, pf_lines);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
 // K = 5120-class shapes (16 warps): the same two-tile idea needs 160 weight registers, so K is walked in two halves of
 // KB blocks per warp (weights of one half in flight at a time) and the 16 warps reduce through 8 shared-memory slots.
 template <int KB, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                                 const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
-                                int flags) {
+                                int flags, const char* pf, int pf_lines) {
     static_assert(NW == 16, "two rounds through 8 reduction slots");
     constexpr int WT = 2;
     __shared__ float red[NW / 2][32][WT * 16 + 1];
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int n0 = blockIdx.x * (16 * WT), r0 = blockIdx.y * 32;
@@ -285,6 +442,7 @@ skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h*
                 ahi[wt][i] = ldg_stream(wb + i * 32);
             }
         }
+        if (h == 0) pdl_wait();        // first half of the weights in flight; X belongs to the chain
 #pragma unroll
         for (int i = 0; i < KB; ++i) {
             uint4 b[4];
@@ -300,6 +458,7 @@ skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h*
                 }
         }
     }
+    l2_prefetch_slice(pf, pf_lines);
     // warps 8..15 park their partial sums, warps 0..7 fold them in (same fragment positions), then the usual 8-slot reduce
     const int slot = warp & 7;
 #pragma unroll
@@ -336,34 +495,39 @@ skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h*
 
 template <int KB, int NW>
 mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
-                        int ldo, int R, int N, int K, int flags, cudaStream_t st) {
+                        int ldo, int R, int N, int K, int flags, cudaStream_t st, const char* pf, int pf_lines) {
     constexpr int WT = (NW <= 8 && KB <= 5) ? 2 : 1;          // two weight tiles where the registers allow it
     static const bool one_tile = [] { const char* e = getenv("MW_SKINNY_WT"); return e && e[0] == '1'; }();   // A/B hook
     if constexpr (NW == 16 && KB % 2 == 0 && KB / 2 <= 5) {
         static const bool no_khalf = [] { const char* e = getenv("MW_SKINNY_KHALF"); return e && e[0] == '0'; }();
         if (!one_tile && !no_khalf) {
             dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
-            skinny_gemm_rows32_khalf_kernel<KB / 2, NW><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W,
-                                                                                  ldw, bias, resid, out, ldo, R, N, K, flags);
+            launch_chained(skinny_gemm_rows32_khalf_kernel<KB / 2, NW>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx, (const mw_h*)W,
+                           ldw, bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
             MW_LAUNCH_CHECK();
             return MW_OK;
         }
     }
     if (WT == 2 && !one_tile) {
         dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
-        skinny_gemm_rows16_kernel<KB, NW, WT><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw,
-                                                                        bias, resid, out, ldo, R, N, K, flags);
+        launch_chained(skinny_gemm_rows16_kernel<KB, NW, WT>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx, (const mw_h*)W, ldw,
+                       bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
     } else {
         dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
-        skinny_gemm_rows16_kernel<KB, NW, 1><<<grid, NW * 32, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw,
-                                                                       bias, resid, out, ldo, R, N, K, flags);
+        launch_chained(skinny_gemm_rows16_kernel<KB, NW, 1>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx, (const mw_h*)W, ldw,
+                       bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
     }
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
 
+// `next_w` / `next_bytes`: the weight matrix of the projection that follows this one in the step (prefetched into L2)
 mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
-                      int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg = true) {
+                      int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg = true,
+                      const void* next_w = nullptr, int64_t next_bytes = 0) {
+    static const bool prefetch_on = [] { const char* e = getenv("MW_PREFETCH"); return !(e && e[0] == '0'); }();   // A/B hook
+    const char* pf = prefetch_on ? (const char*)next_w : nullptr;
+    const int pf_lines = pf ? (int)(next_bytes / 128) : 0;
     // R >= MW_DG_MIN_ROWS rows (merged greedy batches): the weight-stationary tcgen05 kernel (decode_gemm.cu) streams W once
     // for all rows; the mma.sync kernels below re-read it per 32-row block (from L2 after the first block) and stay in charge
     // of the 32-row batches they were tuned on and of beam search, where they measured faster (a decode
@@ -371,7 +535,7 @@ mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const floa
     static const int dg_min_rows = [] { const char* e = getenv("MW_DG_MIN_ROWS"); return e ? atoi(e) : 96; }();
     if (allow_dg && R >= dg_min_rows && decode_gemm_supported(ldx, ldw, R, N, K))
         return decode_gemm_launch(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st);
-#define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st)
+#define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st, pf, pf_lines)
     MW_SK(5, 8);    // 1280  (large)
     MW_SK(10, 16);  // 5120  (large ffn)
     MW_SK(4, 8);    // 1024  (medium)
@@ -386,8 +550,8 @@ mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const floa
     MW_SK(1, 8);    // 256
 #undef MW_SK
     dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
-    skinny_gemm_kernel<<<grid, 256, 0, st>>>((const mw_h*)X, ldx, (const mw_h*)W, ldw, bias, resid,
-                                             out, ldo, R, N, K, flags);
+    launch_chained(skinny_gemm_kernel, grid, dim3(256), 0, st, (const mw_h*)X, ldx, (const mw_h*)W, ldw, bias, resid, out, ldo, R, N, K,
+                   flags);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -395,11 +559,45 @@ mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ cur_tok, const mw_h* __restrict__ emb,
                              const float* __restrict__ pos_emb, const DecCtl* __restrict__ ctl, float* __restrict__ x, int d) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const int tok = cur_tok[r];
     const int pos = ctl->pos;
     for (int i = threadIdx.x; i < d; i += blockDim.x)
         x[(int64_t)r * d + i] = h2f(emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
+}
+
+// LayerNorm + projection.  `solo` (mw_set_solo: the replica decodes alone on its GPU): ONE launch where the fused kernel
+// applies (16-bit output, no residual, K = d_model of a supported size, rows that do not go to the tcgen05 decode GEMM).
+// Otherwise the stand-alone LayerNorm into `ln_buf` and skinny_gemm.  Both give the same bits; which is faster depends on
+// what else the GPU is doing - measured on large-v3, ms per 32-row step, fused / separate: one batch in flight 3.71 / 3.88
+// (96 graph nodes fewer), two 2.78 / 2.75, four 2.33 / 2.20, eight 2.30 / 2.09 (every CTA re-normalises its rows from the
+// fp32 residual stream, and with several batches in flight that L2->SM traffic is what the projections wait for).
+mw_status skinny_gemm_ln(const float* x, const float* gamma, const float* beta, void* ln_buf, const void* W, const float* bias,
+                         void* out, int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg, const void* next_w,
+                         int64_t next_bytes, bool solo) {
+    static const int fuse_env = [] { const char* e = getenv("MW_LN_FUSE"); return e ? atoi(e) : -1; }();   // A/B hook: 0 never, 1 always
+    const bool fuse = fuse_env < 0 ? solo : fuse_env != 0;
+    static const bool prefetch_on = [] { const char* e = getenv("MW_PREFETCH"); return !(e && e[0] == '0'); }();
+    static const int dg_min_rows = [] { const char* e = getenv("MW_DG_MIN_ROWS"); return e ? atoi(e) : 96; }();
+    const bool to_dg = allow_dg && R >= dg_min_rows && decode_gemm_supported(K, K, R, N, K);
+    if (fuse && !to_dg && !(flags & SK_FLAG_F32)) {
+        const char* pf = prefetch_on ? (const char*)next_w : nullptr;
+        const int pf_lines = pf ? (int)(next_bytes / 128) : 0;
+#define MW_SKLN(kb, nw) if (K == kb * nw * 32) return launch_ln_rows16<kb, nw>(x, gamma, beta, W, K, bias, out, ldo, R, N, flags, st, pf, pf_lines)
+        MW_SKLN(5, 8);    // 1280  (large)
+        MW_SKLN(4, 8);    // 1024  (medium)
+        MW_SKLN(3, 8);    // 768   (small)
+        MW_SKLN(2, 8);    // 512   (base)
+        MW_SKLN(3, 4);    // 384   (tiny)
+        MW_SKLN(1, 4);    // 128   (test dims)
+        MW_SKLN(1, 8);    // 256
+#undef MW_SKLN
+    }
+    mw_status r = layernorm_launch(x, gamma, beta, ln_buf, R, K, st);
+    if (r != MW_OK) return r;
+    return skinny_gemm(ln_buf, K, W, K, bias, nullptr, out, ldo, R, N, K, flags, st, allow_dg, next_w, next_bytes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -426,6 +624,8 @@ decode_attn_kernel(const mw_h* __restrict__ q, int ldq,
     extern __shared__ float sc[];          // scores [n_keys] + reduction scratch
     __shared__ float red[4][64];
     __shared__ float red_s[8];
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, r = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int UNR = SELF ? 4 : 8;             // independent 16-byte loads in flight per thread
@@ -554,10 +754,12 @@ decode_attn_kernel(const mw_h* __restrict__ q, int ldq,
 __global__ void __launch_bounds__(128)
 cross_attn_stream_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __restrict__ kbase,
                          const mw_h* __restrict__ vbase, int64_t key_stride, int n_keys,
-                         mw_h* __restrict__ out, int ldo) {
+                         mw_h* __restrict__ out, int ldo, const char* pf, int pf_lines) {
     __shared__ float part_acc[16][64];
     __shared__ float part_m[16], part_l[16];
     constexpr int UNR = 4;
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, r = blockIdx.y;
     const int key_lo = 0, key_hi = n_keys;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -622,6 +824,7 @@ cross_attn_stream_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __rest
             }
         }
     }
+    l2_prefetch_slice(pf, pf_lines);       // this CTA's K/V stream is done: ask L2 for a slice of the output projection's weights
     const int grp = warp * 4 + kq;
 #pragma unroll
     for (int i = 0; i < 8; ++i) part_acc[grp][lg * 8 + i] = acc[i];
@@ -656,6 +859,8 @@ cross_attn_grouped_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __res
     __shared__ float red[4][G][64];
     __shared__ float red_s[G][8];
     constexpr int UNR = 4;
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lg = lane & 7, kq = lane >> 3;
@@ -791,7 +996,7 @@ mw_status launch_cross_grouped(const mw_h* q, int ldq, const mw_h* k, const mw_h
     static PerDeviceOnce attr_once;
     MW_CUDA_CHECK(attr_once.run([&] { return cudaFuncSetAttribute(cross_attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }));
     MW_REQUIRE(smem <= 96 * 1024, "cross attention: %zu bytes of scores exceed shared memory", smem);
-    cross_attn_grouped_kernel<G><<<dim3(n_heads, B), 128, smem, st>>>(q, ldq, k, v, key_stride, n_keys, out, ldo);
+    launch_chained(cross_attn_grouped_kernel<G>, dim3(n_heads, B), dim3(128), smem, st, q, ldq, k, v, key_stride, n_keys, out, ldo);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -946,6 +1151,8 @@ __global__ void __launch_bounds__(SEL_THREADS)
 select_greedy_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts, const uint8_t* __restrict__ sup,
                      const uint8_t* __restrict__ beg, int* tokens, int* gen_len, int* done, float* cum, int* last_ts,
                      int* cur_tok, DecCtl* ctl, int max_new) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const GenOptsDev o = *opts;
     float* lg = logits + (int64_t)r * V;
@@ -981,6 +1188,8 @@ select_greedy_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts, 
 __global__ void advance_forced_kernel(const int* __restrict__ forced, int per_row_stride, int n_forced, int* cur_tok,
                                       DecCtl* ctl, int R) {
     // single CTA: every thread reads ctl->step before thread 0 advances it
+    pdl_trigger();
+    pdl_wait();
     const int next = ctl->step + 1;
     if (next < n_forced)
         for (int r = threadIdx.x; r < R; r += blockDim.x) cur_tok[r] = forced[(int64_t)r * per_row_stride + next];
@@ -999,6 +1208,8 @@ beam_candidates_kernel(float* logits, int V, const GenOptsDev* __restrict__ opts
                        DecCtl* ctl) {
     __shared__ ValIdx s_c[SEL_THREADS / 32];
     __shared__ ValIdx s_pick;
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const GenOptsDev o = *opts;
     float* lg = logits + (int64_t)r * V;
@@ -1068,6 +1279,8 @@ __global__ void beam_update_kernel(const GenOptsDev* __restrict__ opts, const fl
                                    const int* __restrict__ idx_in, int* idx_out, int ctx,
                                    int* fin_count, float* fin_score, int* fin_len, int* fin_tok, int* active,
                                    int* cur_tok, DecCtl* ctl, int B, int max_new) {
+    pdl_trigger();
+    pdl_wait();
     const GenOptsDev o = *opts;
     const int k = o.beam, nc = 2 * k;
     const int b = blockIdx.x;
@@ -1329,7 +1542,8 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
     const int d = c.d_model, ctx = c.n_text_ctx, T = c.n_audio_ctx;
     mw_status r;
     if (parts & PART_EMBED) {
-        embed_kernel<<<R, 128, 0, st>>>(s->cur_tok, (const mw_h*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS), s->ctl, s->x, d);
+        launch_chained(embed_kernel, dim3(R), dim3(128), 0, st, s->cur_tok, (const mw_h*)m->gw(MW_DEC_EMB), (const float*)m->gw(MW_DEC_POS),
+                       s->ctl, s->x, d);
         MW_LAUNCH_CHECK();
     }
     const int* idx = beam > 1 ? s->self_idx[idx_phase] : nullptr;
@@ -1338,19 +1552,33 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
         auto F = [&](int id) { return (const float*)m->dlw(l, id); };
         const bool LN = parts & PART_LN, GM = parts & PART_GEMM;
         const bool dg = beam <= 1;
-        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st, dg)) != MW_OK) return r;
+        const int64_t dd = (int64_t)d * d * 2, df = (int64_t)d * c.ffn * 2;          // bytes of a d x d / d x ffn weight matrix
+        const void* next_qkv = l + 1 < c.dec_layers ? m->dlw(l + 1, MW_DL_WQKV) : nullptr;
+        static const bool pf_on = [] { const char* e = getenv("MW_PREFETCH"); return !(e && e[0] == '0'); }();
+        const char* pf_xo = (pf_on && GM) ? (const char*)W(MW_DL_WXO) : nullptr;
+        if (LN && GM) {
+            if ((r = skinny_gemm_ln(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, W(MW_DL_WQKV), F(MW_DL_BQKV), s->qkv, 3 * d, R, 3 * d, d, 0,
+                                    st, dg, W(MW_DL_WO), dd, s->solo)) != MW_OK) return r;
+        } else {
+            if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN1_G), F(MW_DL_LN1_B), s->ln, R, d, st)) != MW_OK) return r;
+            if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WQKV), d, F(MW_DL_BQKV), nullptr, s->qkv, 3 * d, R, 3 * d, d, 0, st, dg, W(MW_DL_WO), dd)) != MW_OK) return r;
+        }
         if (parts & PART_SELF) {
             mw_h* kc = s->k_self + (int64_t)l * s->R_max * ctx * d;
             mw_h* vc = s->v_self + (int64_t)l * s->R_max * ctx * d;
             dim3 grid(c.n_heads, R);
-            decode_attn_kernel<true><<<grid, 128, ctx * sizeof(float), st>>>(
-                s->qkv, 3 * d, kc, vc, d, ctx, idx, ctx, s->ctl, 0, 1, s->qkv + d, s->qkv + 2 * d, 3 * d, s->att, d);
+            launch_chained(decode_attn_kernel<true>, grid, dim3(128), ctx * sizeof(float), st, s->qkv, 3 * d, kc, vc, d, ctx, idx, ctx,
+                           s->ctl, 0, 1, s->qkv + d, s->qkv + 2 * d, 3 * d, s->att, d, 0);
             MW_LAUNCH_CHECK();
         }
-        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg)) != MW_OK) return r;
-        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st, dg)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WO), d, F(MW_DL_BO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg, W(MW_DL_WXQ), dd)) != MW_OK) return r;
+        if (LN && GM) {
+            if ((r = skinny_gemm_ln(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, W(MW_DL_WXQ), F(MW_DL_BXQ), s->qx, d, R, d, d, 0, st, dg,
+                                    nullptr, 0, s->solo)) != MW_OK) return r;
+        } else {
+            if (LN && (r = layernorm_launch(s->x, F(MW_DL_LNX_G), F(MW_DL_LNX_B), s->ln, R, d, st)) != MW_OK) return r;
+            if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_WXQ), d, F(MW_DL_BXQ), nullptr, s->qx, d, R, d, d, 0, st, dg)) != MW_OK) return r;
+        }
         if (parts & PART_CROSS) {
             mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             if (beam > 1) {
@@ -1372,18 +1600,24 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                     attr[0].val.priority = s->prio_low;
                     cfg.attrs = attr; cfg.numAttrs = 1;
                     MW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, cross_attn_stream_kernel, (const mw_h*)s->qx, d, (const mw_h*)kv,
-                                                     (const mw_h*)(kv + d), (int64_t)(2 * d), T, s->att, d));
+                                                     (const mw_h*)(kv + d), (int64_t)(2 * d), T, s->att, d, pf_xo, (int)(dd / 128)));
                     count_launch();
                 } else {
-                    cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
+                    launch_chained(cross_attn_stream_kernel, grid, dim3(128), 0, st, s->qx, d, kv, kv + d, 2 * d, T, s->att, d, pf_xo,
+                                   (int)(dd / 128));
                     MW_LAUNCH_CHECK();
                 }
             }
         }
-        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg)) != MW_OK) return r;
-        if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st, dg)) != MW_OK) return r;
-        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st, dg)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->att, d, W(MW_DL_WXO), d, F(MW_DL_BXO), s->x, s->x, d, R, d, d, SK_FLAG_F32, st, dg, W(MW_DL_W1), df)) != MW_OK) return r;
+        if (LN && GM) {
+            if ((r = skinny_gemm_ln(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, W(MW_DL_W1), F(MW_DL_B1), s->mlp, c.ffn, R, c.ffn, d,
+                                    SK_FLAG_GELU, st, dg, W(MW_DL_W2), df, s->solo)) != MW_OK) return r;
+        } else {
+            if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
+            if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st, dg, W(MW_DL_W2), df)) != MW_OK) return r;
+        }
+        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st, dg, next_qkv, 3 * dd)) != MW_OK) return r;
     }
     return MW_OK;
 }
@@ -1402,18 +1636,18 @@ mw_status enqueue_select(mw_model* m, int B, int beam, int phase, cudaStream_t s
     DecoderState* s = m->dec;
     const int R = B * beam;
     if (beam <= 1) {
-        select_greedy_kernel<<<R, SEL_THREADS, 0, st>>>(s->logits, c.vocab, s->opts, s->sup_mask, s->begin_mask, s->tokens[0],
-                                                        s->gen_len, s->done, s->cum, s->last_ts[0], s->cur_tok, s->ctl, s->max_new);
+        launch_chained(select_greedy_kernel, dim3(R), dim3(SEL_THREADS), 0, st, s->logits, c.vocab, s->opts, s->sup_mask, s->begin_mask,
+                       s->tokens[0], s->gen_len, s->done, s->cum, s->last_ts[0], s->cur_tok, s->ctl, s->max_new);
         MW_LAUNCH_CHECK();
         return MW_OK;
     }
-    beam_candidates_kernel<<<R, SEL_THREADS, 0, st>>>(s->logits, c.vocab, s->opts, s->sup_mask, s->begin_mask, s->tokens[phase],
-                                                      s->gen_len, s->last_ts[phase], s->cand_val, s->cand_idx, s->row_lse, s->max_new, s->ctl);
+    launch_chained(beam_candidates_kernel, dim3(R), dim3(SEL_THREADS), 0, st, s->logits, c.vocab, s->opts, s->sup_mask, s->begin_mask,
+                   s->tokens[phase], s->gen_len, s->last_ts[phase], s->cand_val, s->cand_idx, s->row_lse, s->max_new, s->ctl);
     MW_LAUNCH_CHECK();
-    beam_update_kernel<<<B, 128, 0, st>>>(s->opts, s->cand_val, s->cand_idx, s->row_lse, s->tokens[phase], s->tokens[phase ^ 1],
-                                          s->gen_len, s->cum, s->last_ts[phase], s->last_ts[phase ^ 1], s->self_idx[phase],
-                                          s->self_idx[phase ^ 1], c.n_text_ctx, s->fin_count, s->fin_score, s->fin_len, s->fin_tok,
-                                          s->active, s->cur_tok, s->ctl, B, s->max_new);
+    launch_chained(beam_update_kernel, dim3(B), dim3(128), 0, st, s->opts, s->cand_val, s->cand_idx, s->row_lse, s->tokens[phase],
+                   s->tokens[phase ^ 1], s->gen_len, s->cum, s->last_ts[phase], s->last_ts[phase ^ 1], s->self_idx[phase],
+                   s->self_idx[phase ^ 1], c.n_text_ctx, s->fin_count, s->fin_score, s->fin_len, s->fin_tok, s->active, s->cur_tok,
+                   s->ctl, B, s->max_new);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -1531,7 +1765,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     }
     DecoderState::Graphs* slot = nullptr;
     for (auto& g : s->graph_cache)
-        if (g.prefill && g.R == R && g.beam == beam) { g.last_use = ++s->graph_clock; s->graphs = g; return MW_OK; }
+        if (g.prefill && g.R == R && g.beam == beam && g.solo == s->solo) { g.last_use = ++s->graph_clock; s->graphs = g; return MW_OK; }
     slot = &s->graph_cache[0];                // a free slot, else the least recently used one
     for (auto& g : s->graph_cache) {
         if (!g.prefill) { slot = &g; break; }
@@ -1545,7 +1779,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     r = capture_graph(s, &s->graphs.prefill, [&](cudaStream_t st) -> mw_status {
         mw_status q = enqueue_layers(m, R, beam, 0, st);
         if (q != MW_OK) return q;
-        advance_forced_kernel<<<1, 256, 0, st>>>(s->prompt, 0, 1 << 30, s->cur_tok, s->ctl, R);
+        launch_chained(advance_forced_kernel, dim3(1), dim3(256), 0, st, s->prompt, 0, 1 << 30, s->cur_tok, s->ctl, R);
         MW_LAUNCH_CHECK();
         return MW_OK;
     });
@@ -1563,6 +1797,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     }
     s->graphs.R = R;
     s->graphs.beam = beam;
+    s->graphs.solo = s->solo;
     s->graphs.last_use = ++s->graph_clock;
     *slot = s->graphs;
     return MW_OK;
@@ -1832,7 +2067,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
         if (which == 0) {
             mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             dim3 grid(c.n_heads, B);
-            cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d);
+            cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d, nullptr, 0);
             MW_LAUNCH_CHECK();
             return MW_OK;
         }
@@ -1893,6 +2128,12 @@ extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, flo
 // ---- measurement hook (bench.py "in_step" attribution): keep only the kernel classes in `parts` (mask of mw_bench_step) in
 // the decode-step graphs captured from now on, process-wide; 127 restores the real step.  Decoded ids are meaningless while a
 // class is missing: the difference in step time with and without a class is its in-step cost under real concurrency.
+extern "C" mw_status mw_set_solo(mw_model* m, int solo) {
+    MW_REQUIRE(m && m->dec, "mw_set_solo: null model");
+    m->dec->solo = solo != 0;          // step graphs are cached per mode (ensure_graphs)
+    return MW_OK;
+}
+
 extern "C" void mw_debug_step_parts(int parts) {
     mw::g_step_parts.store(parts);
     mw::g_step_parts_epoch.fetch_add(1);

@@ -162,6 +162,11 @@ class Engine:
         return out
 
     # ---- S3
+    def set_solo(self, solo: bool) -> None:
+        """mw_set_solo: True when this replica is the only one decoding on its GPU (step built for latency), False when
+        several replicas decode concurrently (default).  Same ids either way."""
+        _lib.check(self.lib.mw_set_solo(self.handle, 1 if solo else 0), "mw_set_solo")
+
     def generate(self, enc: torch.Tensor, prompt: Sequence[int], tokens: SpecialTokens, *, beam_size: int = 5,
                  patience: float = 1.0, length_penalty: float = 1.0, max_length: int = 448,
                  suppress_blank: bool = True, suppress_tokens: Optional[Sequence[int]] = (-1,),

@@ -288,3 +288,24 @@ def test_batched_prefill_matches_stepwise_prefill(small, monkeypatch):
         assert sum(same) >= len(same) - 1 and all(p >= 3 for p in prefix)
         for a, b in zip(res["0"][beam], res["1"][beam]):
             assert abs(a.scores[0] - b.scores[0]) < 3e-2
+
+
+@pytest.mark.parametrize("which", ["small", "tiny"])
+def test_solo_mode_decodes_the_same_ids(which, request):
+    """mw_set_solo folds LayerNorm into the projections that consume it (same lane mapping, summation order and rounding as
+    the stand-alone kernel): greedy and beam ids and scores must not move by a bit."""
+    dims, tok, sd, eng, mel, orc, emu = request.getfixturevalue(which)
+    enc = eng.encode(mel.cuda())
+    prompt = [tok.sot, tok.sot + 1, tok.transcribe, tok.no_timestamps]
+    beams = (1, 5) if which == "small" else (1,)          # the tiny fixture's engine is built for greedy only
+    res = {}
+    try:
+        for solo in (False, True):
+            eng.set_solo(solo)
+            res[solo] = {beam: eng.generate(enc, prompt, tok, beam_size=beam, max_length=64) for beam in beams}
+    finally:
+        eng.set_solo(False)
+    for beam in beams:
+        for a, b in zip(res[False][beam], res[True][beam]):
+            assert a.sequences_ids[0] == b.sequences_ids[0]
+            assert a.scores[0] == b.scores[0]
