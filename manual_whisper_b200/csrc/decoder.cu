@@ -572,8 +572,10 @@ __global__ void embed_kernel(const int* __restrict__ cur_tok, const mw_h* __rest
 // applies (16-bit output, no residual, K = d_model of a supported size, rows that do not go to the tcgen05 decode GEMM).
 // Otherwise the stand-alone LayerNorm into `ln_buf` and skinny_gemm.  Both give the same bits; which is faster depends on
 // what else the GPU is doing - measured on large-v3, ms per 32-row step, fused / separate: one batch in flight 3.71 / 3.88
-// (96 graph nodes fewer), two 2.78 / 2.75, four 2.33 / 2.20, eight 2.30 / 2.09 (every CTA re-normalises its rows from the
-// fp32 residual stream, and with several batches in flight that L2->SM traffic is what the projections wait for).
+// (96 graph nodes fewer), two 2.78 / 2.75, four 2.33 / 2.20, eight 2.30 / 2.09.  With several batches in flight a node's
+// fixed cost is hidden by the other batches anyway, and every CTA now holds its SM slot (and 84 KB of shared memory) for the
+// ~1 us it spends normalising 32 rows before it asks for its weights.  (It is not the extra L2->SM traffic: reading the
+// 16-bit operand twice in the plain kernels costs nothing at eight streams.)
 mw_status skinny_gemm_ln(const float* x, const float* gamma, const float* beta, void* ln_buf, const void* W, const float* bias,
                          void* out, int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg, const void* next_w,
                          int64_t next_bytes, bool solo) {
