@@ -85,7 +85,7 @@ struct DecoderState {
     // step graphs are specific to (rows, beam): a small cache keeps the last few shapes (full batches and the short
     // last batch of a recording alternate) so they are not re-captured on every call
     bool solo = false;                   // mw_set_solo: this replica decodes alone on its GPU (latency mode, see skinny_gemm_ln)
-    struct Graphs { int R = 0, beam = 0; bool solo = false; uint64_t last_use = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
+    struct Graphs { int R = 0, beam = 0; bool solo = false; int n_prefill = 0, n_gen[2] = {0, 0}; uint64_t last_use = 0; cudaGraphExec_t prefill = nullptr, gen[2] = {nullptr, nullptr}; };
     static constexpr int GRAPH_CACHE = 4;
     Graphs graph_cache[GRAPH_CACHE];
     uint64_t graph_clock = 0;
@@ -1655,12 +1655,14 @@ mw_status enqueue_select(mw_model* m, int B, int beam, int phase, cudaStream_t s
 }
 
 template <typename Fn>
-mw_status capture_graph(DecoderState* s, cudaGraphExec_t* out, Fn&& enqueue) {
+mw_status capture_graph(DecoderState* s, cudaGraphExec_t* out, int* n_nodes, Fn&& enqueue) {
     cudaGraph_t graph = nullptr;
     MW_CUDA_CHECK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const uint64_t launches_before = g_launches.load();
+    t_capturing = true;                      // captured launches are counted when the graph is replayed
+    t_captured = 0;
     mw_status r = enqueue(s->cap_stream);
-    g_launches.store(launches_before);       // captured launches are counted when the graph is replayed
+    t_capturing = false;
+    *n_nodes = (int)t_captured;
     cudaError_t e = cudaStreamEndCapture(s->cap_stream, &graph);
     if (r != MW_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return MW_ERR_CUDA; }
@@ -1753,8 +1755,6 @@ mw_status batched_prefill(mw_model* m, int B, int beam, int Pm, cudaStream_t st)
     return MW_OK;
 }
 
-int launches_per_layers(const mw_model_config& c) { return 1 + c.dec_layers * 11; }
-
 std::atomic<int> g_step_parts{[] { const char* e = getenv("MW_STEP_PARTS"); return e ? atoi(e) : (int)PART_ALL; }()};
 std::atomic<int> g_step_parts_epoch{0};
 
@@ -1778,7 +1778,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     mw_status r;
     // prefill step: layers + forced advance.  With beam search the prefill rows are their own ancestors, so the
     // identity index table (phase 0) is used.
-    r = capture_graph(s, &s->graphs.prefill, [&](cudaStream_t st) -> mw_status {
+    r = capture_graph(s, &s->graphs.prefill, &s->graphs.n_prefill, [&](cudaStream_t st) -> mw_status {
         mw_status q = enqueue_layers(m, R, beam, 0, st);
         if (q != MW_OK) return q;
         launch_chained(advance_forced_kernel, dim3(1), dim3(256), 0, st, s->prompt, 0, 1 << 30, s->cur_tok, s->ctl, R);
@@ -1789,7 +1789,7 @@ mw_status ensure_graphs(mw_model* m, int B, int beam) {
     for (int phase = 0; phase < (beam > 1 ? 2 : 1); ++phase) {
         // measurement only (mw_debug_step_parts / MW_STEP_PARTS; ids are then meaningless): kernel classes kept in the step graph
         const int step_parts = g_step_parts.load();
-        r = capture_graph(s, &s->graphs.gen[phase], [&](cudaStream_t st) -> mw_status {
+        r = capture_graph(s, &s->graphs.gen[phase], &s->graphs.n_gen[phase], [&](cudaStream_t st) -> mw_status {
             mw_status q = enqueue_layers(m, R, beam, phase, st, step_parts);
             if (q != MW_OK) return q;
             if ((q = enqueue_logits(m, R, st)) != MW_OK) return q;
@@ -1907,8 +1907,6 @@ extern "C" mw_status mw_generate(mw_model* m, const void* d_enc, int B, const in
     if ((r = cross_kv_project(m, d_enc, B, st)) != MW_OK) return r;
     if ((r = reset_state(m, B, beam, h_prompt, prompt_len, opt, prompt_len - 1, max_new, st)) != MW_OK) return r;
     if ((r = ensure_graphs(m, B, beam)) != MW_OK) return r;
-    const int per_prefill = launches_per_layers(c) + 1;
-    const int per_gen = launches_per_layers(c) + 2 + (beam > 1 ? 2 : 1);
     const int Pm = prompt_len - 1;
     const char* force_stepwise = getenv("MW_STEPWISE_PREFILL");      // test hook: compare the two prefill paths
     if (Pm >= 4 && Pm <= c.n_audio_ctx && !(force_stepwise && force_stepwise[0] == '1')) {
@@ -1916,7 +1914,7 @@ extern "C" mw_status mw_generate(mw_model* m, const void* d_enc, int B, const in
     } else {
         for (int i = 0; i < Pm; ++i) {
             MW_CUDA_CHECK(cudaGraphLaunch(s->graphs.prefill, st));
-            count_launch(per_prefill);
+            count_launch(s->graphs.n_prefill);        // nodes counted when the graph was captured
         }
     }
     // generation: the finished counter is polled one window late so the stream never drains
@@ -1926,7 +1924,7 @@ extern "C" mw_status mw_generate(mw_model* m, const void* d_enc, int B, const in
     bool stop = false;
     for (int step = 0; step < max_new && !stop; ++step) {
         MW_CUDA_CHECK(cudaGraphLaunch(s->graphs.gen[beam > 1 ? (step & 1) : 0], st));
-        count_launch(per_gen);
+        count_launch(s->graphs.n_gen[beam > 1 ? (step & 1) : 0]);
         if ((step + 1) % window == 0 && step + 1 < max_new) {
             MW_CUDA_CHECK(cudaMemcpyAsync(&s->h_ctl[w & 1], s->ctl, sizeof(DecCtl), cudaMemcpyDeviceToHost, st));
             MW_CUDA_CHECK(cudaEventRecord(s->ev[w & 1], st));
@@ -2104,7 +2102,8 @@ extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, flo
     MW_CUDA_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(DecCtl), st));
     MW_CUDA_CHECK(cudaMemsetAsync(s->cur_tok, 0, B * 4, st));
     cudaGraphExec_t g = nullptr;
-    mw_status r = capture_graph(s, &g, [&](cudaStream_t cs) -> mw_status {
+    int n_nodes = 0;
+    mw_status r = capture_graph(s, &g, &n_nodes, [&](cudaStream_t cs) -> mw_status {
         mw_status q = enqueue_layers(m, B, 1, 0, cs, parts);
         if (q != MW_OK) return q;
         if ((parts & PART_LOGITS) && (q = enqueue_logits(m, B, cs)) != MW_OK) return q;
@@ -2117,6 +2116,7 @@ extern "C" mw_status mw_bench_step(mw_model* m, int B, int parts, int iters, flo
     for (int i = 0; i < 2; ++i) MW_CUDA_CHECK(cudaGraphLaunch(g, st));
     MW_CUDA_CHECK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i) MW_CUDA_CHECK(cudaGraphLaunch(g, st));
+    count_launch((iters + 2) * n_nodes);
     MW_CUDA_CHECK(cudaEventRecord(e1, st));
     MW_CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;

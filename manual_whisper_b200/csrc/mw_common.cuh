@@ -50,7 +50,14 @@ namespace mw {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 
-inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+// Launches enqueued while this thread captures a CUDA graph are not launches yet: they are tallied per graph
+// (t_captured) and added to g_launches each time the graph is replayed.
+extern thread_local bool t_capturing;
+extern thread_local uint64_t t_captured;
+inline void count_launch(int n = 1) {
+    if (t_capturing) t_captured += (uint64_t)n;
+    else g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+}
 
 // Programmatic dependent launch (the decode step is a chain of ~350 short dependent kernels): a kernel launched through
 // launch_chained() may be scheduled while its predecessor in the stream is still running.  It calls pdl_trigger() first (its
