@@ -599,6 +599,30 @@ def main():
     ms_w, audio_w, _, _ = throughput_steps(own_res, oo, ol.astype(np.int32), ol, args.steps)
     ms_w_max = allreduce([ms_w], "max")[0]
     audio_w_sum = allreduce([audio_w], "sum")[0]
+    # config 5 at N GPUs: independent replicas, every rank the un-chunked log-mel of its own 1-hour clip (no exchange needed)
+    lm = None
+    if not args.no_extras:
+        from manual_whisper_b200 import audio as A
+        g = torch.Generator(device=model.device).manual_seed(5 + rank)
+        hour = torch.randn(int(HOUR_S) * 16000, device=model.device, generator=g) * 0.1
+        plan = A.get_plan(dims.n_mels, model.device)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=model.device)
+        for _ in range(3):
+            plan.long(hour, padding=0)
+        t = []
+        for _ in range(5):
+            flush.fill_(1)
+            e0, e1 = _events()
+            e0.record(); plan.long(hour, padding=0); e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        peaks = _peaks()
+        lm_ms = allreduce([statistics.median(t)], "max")[0]
+        nb = world * (4 * hour.numel() + 4 * dims.n_mels * (hour.numel() // 160))
+        lm = {"unchunked_1h_per_gpu": {"ms": lm_ms, "GBps": nb / lm_ms / 1e6, "frac_of_hbm": nb / lm_ms / 1e6 / (world * peaks["hbm"]),
+                                       "bytes": nb, "what": f"config 5 at {world} GPUs: independent replicas, each rank log_mel_spectrogram("
+                                                            "audio[1 h], padding=0) of its own clip; total algorithmic bytes / max time over ranks"}}
+        del hour, flush
     if rank == 0:
         per_rank = [len(s) for s in shard_windows(lens, world)]
         config["parallelism"] = (f"dp{world}: ONE recording, {len(windows)} windows sharded {min(per_rank)}-{max(per_rank)} per GPU "
@@ -607,13 +631,16 @@ def main():
                      "config": config, "clocks": clocks, "gpu_launches": int(launches_all),
                      "ids_match_single_gpu": bool(match),
                      "limiting_factor": "each GPU holds under-filled batches (windows per GPU <= a few batches of 32): the 224 decode steps "
-                                        "are a serial chain of ~360 latency-bound launches (~3.5 ms per step however few rows), so the time "
-                                        "of a pass stops falling once a GPU holds a single batch; no collective is involved",
+                                        "are a serial chain of graph nodes at >= 3.3 us each (~260 nodes, ~3.3 ms per step however few rows, "
+                                        "with LayerNorm folded into the projections when a GPU holds a single batch: mw_set_solo), so the "
+                                        "time of a pass stops falling once a GPU holds a single batch; no collective is involved",
                      "e2e": {"value": HOUR_S / e2e_s, "unit": "x real-time", "h2d_bytes_per_step": int(h2d),
                              "d2h_bytes_per_step": len(windows) * MAX_NEW * 4, "seconds_per_hour_of_audio": e2e_s,
                              "api": "manual_whisper_b200.distributed.transcribe_sharded(pipe, host_audio, 32, rank, world)"},
                      "weak": {"value": audio_w_sum / (ms_w_max / 1e3), "unit": "x real-time", "ms_per_step": ms_w_max / args.steps,
                               "what": "every rank transcribes its OWN 1-hour recording (batches of 32, 8 in flight): total audio / max time"}})
+        if lm:
+            line["logmel"] = lm
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -338,7 +338,8 @@ class FasterWhisperPipeline:
                 with torch.cuda.device(rep.device):
                     if batch_size > rep.engine.max_batch:
                         raise ValueError(f"batch_size={batch_size} exceeds the replica's max_batch={rep.engine.max_batch}")
-                    rep.engine.set_solo(n_rep == 1)      # one batch in flight on this GPU: build the decode step for latency
+                    # the only replica working on its GPU for this job: build the decode step for latency (mw_set_solo)
+                    rep.engine.set_solo(sum(1 for r in self.replicas[:n_rep] if r.device == rep.device) == 1)
                     stream = rep.stream if (rep.stream is not None and n_rep > 1) else torch.cuda.current_stream(rep.device)
                     d_audio = resident["audio"][rep.device]
                     with torch.cuda.stream(stream):
