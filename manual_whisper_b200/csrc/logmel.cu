@@ -11,6 +11,7 @@
 #include "mw_common.cuh"
 #include "logmel_core.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace mw::logmel;
@@ -28,6 +29,7 @@ struct TileSmem {
     cpx tw200[200];           // 1600 B
     cpx tw400[N_FREQ + 1];    // 1616 B
     float red[NT / 32];
+    float red_min[NT / 32];
     // sparse filterbank, resident for the CTA's lifetime (a warp walks one mel row at a time: keeping these in
     // shared memory removes a chain of dependent global loads per row)
     int mel_lo[MAX_SM_MELS], mel_cnt[MAX_SM_MELS], mel_off[MAX_SM_MELS];
@@ -51,7 +53,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
                    const float* __restrict__ tables,   // win[400] | tw200[200*2] | tw400[202*2]
                    const int* __restrict__ mel_lo, const int* __restrict__ mel_cnt,
                    const int* __restrict__ mel_off, const float* __restrict__ mel_w, int mel_nnz,
-                   float* __restrict__ out, unsigned* __restrict__ gmax) {
+                   float* __restrict__ out, unsigned* __restrict__ gmax, float* __restrict__ tile_min /* null: store unscaled */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -95,17 +97,22 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t n_audio,
         __syncthreads();
         stage_power(tid, s.Y, s.tw400, s.P);
         __syncthreads();
+        float vmin = INFINITY;
         float vmax = stage_mel(tid, s.P, n_mels, p_lo, p_cnt, p_off, p_w, out + (int64_t)chunk * n_mels * n_frames, n_frames,
-                               frame0, n_frames, -INFINITY);
+                               frame0, n_frames, -INFINITY, tile_min ? &vmin : nullptr);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        if ((tid & 31) == 0) s.red[tid >> 5] = vmax;
+        for (int o = 16; o > 0; o >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        }
+        if ((tid & 31) == 0) { s.red[tid >> 5] = vmax; s.red_min[tid >> 5] = vmin; }
         __syncthreads();
         if (tid == 0) {
-            float m = s.red[0];
+            float m = s.red[0], mn = s.red_min[0];
 #pragma unroll
-            for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, s.red[w]);
+            for (int w = 1; w < NT / 32; ++w) { m = fmaxf(m, s.red[w]); mn = fminf(mn, s.red_min[w]); }
             atomicMax(gmax + chunk, ordered_bits(m));
+            if (tile_min) tile_min[t] = mn;
         }
         // the next tile's first shared-memory writes (stage) are separated from this tile's last reads (P, red) by
         // the barrier above and the one after its load stage
@@ -153,6 +160,23 @@ logmel_finalize_kernel(float* __restrict__ out, const unsigned* __restrict__ gma
     }
 }
 
+// Un-chunked path: the tile kernel stored (v + 4) / 4 already and left every tile's minimum behind; only tiles holding a value
+// below max - 8 have anything to clamp (noise-like audio: a handful per hour, by extreme-value statistics; digital silence: all
+// of them).  One CTA per tile of 32 frames; the others return at once.
+__global__ void __launch_bounds__(256)
+logmel_clamp_scaled_kernel(float* __restrict__ out, const unsigned* __restrict__ gmax, const float* __restrict__ tile_min, int n_mels,
+                           int64_t n_frames) {
+    const float g = from_ordered_bits(gmax[0]);
+    if (tile_min[blockIdx.x] >= g - 8.0f) return;
+    const int64_t f0 = (int64_t)blockIdx.x * FR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (f0 + lane >= n_frames) return;
+    for (int m = warp; m < n_mels; m += 8) {
+        float* o = out + (int64_t)m * n_frames + f0 + lane;
+        *o = clamp_scaled(*o, g);
+    }
+}
+
 }  // namespace
 
 struct mw_logmel_plan {
@@ -167,6 +191,8 @@ struct mw_logmel_plan {
     int nnz = 0;
     int sm_count = 148;
     unsigned* d_gmax = nullptr;
+    float* d_tile_min = nullptr;         // un-chunked path only: per-tile minimum, grown on demand
+    int64_t tile_min_cap = 0;
 };
 
 extern "C" mw_status mw_logmel_plan_create(int n_mels, const float* h_filters, int max_chunks, int device,
@@ -228,7 +254,7 @@ extern "C" void mw_logmel_plan_destroy(mw_logmel_plan* p) {
     if (!p) return;
     mw::DeviceGuard guard(p->device);
     cudaFree(p->d_tables); cudaFree(p->d_lo); cudaFree(p->d_cnt); cudaFree(p->d_off);
-    cudaFree(p->d_w); cudaFree(p->d_gmax);
+    cudaFree(p->d_w); cudaFree(p->d_gmax); cudaFree(p->d_tile_min);
     delete p;
 }
 
@@ -241,14 +267,29 @@ static mw_status run_logmel(mw_logmel_plan* p, const float* d_audio, int64_t n_a
     MW_REQUIRE(tiles <= 2147483647LL, "mw_logmel: clip too long");
     mw::DeviceGuard guard(p->device);
     MW_CUDA_CHECK(cudaMemsetAsync(p->d_gmax, 0, n_chunks * sizeof(unsigned), st));
+    // one un-chunked clip with no time-major copy wanted (mw_logmel_long): values are stored scaled and the second pass over
+    // the output runs only if the clamp has anything to do
+    const bool scaled = !d_offsets && !d_out_t && n_chunks == 1;
+    if (scaled && tiles > p->tile_min_cap) {          // first call at this length (the only allocation this path ever makes)
+        MW_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(p->d_tile_min);
+        p->d_tile_min = nullptr;
+        p->tile_min_cap = 0;
+        MW_CUDA_CHECK(cudaMalloc(&p->d_tile_min, tiles * sizeof(float)));
+        p->tile_min_cap = tiles;
+    }
     dim3 grid((unsigned)tiles, (unsigned)n_chunks);
     const int64_t total_tiles = tiles * n_chunks;
     const unsigned persistent = (unsigned)(total_tiles < 2LL * p->sm_count ? total_tiles : 2LL * p->sm_count);
     logmel_tile_kernel<<<persistent, NT, sizeof(TileSmem), st>>>(d_audio, n_audio, d_offsets, d_lengths, single_len, padded,
                                                                 n_frames, p->n_mels, n_chunks, p->d_tables, p->d_lo, p->d_cnt,
-                                                                p->d_off, p->d_w, p->nnz, d_out, p->d_gmax);
+                                                                p->d_off, p->d_w, p->nnz, d_out, p->d_gmax, scaled ? p->d_tile_min : nullptr);
     MW_LAUNCH_CHECK();
-    logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (mw_h*)d_out_t);
+    if (scaled) {
+        logmel_clamp_scaled_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_out, p->d_gmax, p->d_tile_min, p->n_mels, n_frames);
+    } else {
+        logmel_finalize_kernel<<<grid, 256, 0, st>>>(d_out, p->d_gmax, p->n_mels, n_frames, (mw_h*)d_out_t);
+    }
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

@@ -224,10 +224,11 @@ MW_HD float fast_log10(float x) {
 }
 
 // ---- stage 4: sparse mel projection + log10, one lane per frame -----------------------------------
-// returns the thread's running max of the values it produced (for valid frames)
+// returns the thread's running max of the values it produced (for valid frames).  `vmin` (optional): running min as well, and
+// the value is then stored already scaled, (v + 4) / 4 - the un-chunked path, whose clamp pass is skipped when min >= max - 8.
 MW_HD float stage_mel(int tid, const float* P, int n_mels, const int* mel_lo, const int* mel_cnt,
                       const int* mel_off, const float* mel_w, float* out, int64_t out_stride,
-                      int64_t frame0, int64_t n_frames, float vmax) {
+                      int64_t frame0, int64_t n_frames, float vmax, float* vmin = nullptr) {
     const int lane = tid & 31, warp = tid >> 5;
     const float* p = P + lane * PS;
     const bool valid = frame0 + lane < n_frames;
@@ -238,14 +239,17 @@ MW_HD float stage_mel(int tid, const float* P, int n_mels, const int* mel_lo, co
         for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], p[lo + i], acc);
         const float v = fast_log10(fmaxf(acc, 1e-10f));
         if (valid) {
-            out[(int64_t)m * out_stride + frame0 + lane] = v;
+            out[(int64_t)m * out_stride + frame0 + lane] = vmin ? (v + 4.0f) / 4.0f : v;
             vmax = fmaxf(vmax, v);
+            if (vmin) *vmin = fminf(*vmin, v);
         }
     }
     return vmax;
 }
 
 MW_HD float finalize_value(float v, float gmax) { return (fmaxf(v, gmax - 8.0f) + 4.0f) / 4.0f; }
+// the same value from an already scaled w = (v + 4) / 4: x -> (x + 4) / 4 is monotone, so max commutes with it exactly
+MW_HD float clamp_scaled(float w, float gmax) { return fmaxf(w, ((gmax - 8.0f) + 4.0f) / 4.0f); }
 
 }  // namespace logmel
 }  // namespace mw

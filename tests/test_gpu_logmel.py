@@ -105,3 +105,22 @@ def test_chunk_equals_unchunked_on_the_same_slice(dev):
     c = plan.chunks(d, torch.tensor([4321], device=dev), torch.tensor([200000], dtype=torch.int32, device=dev))[0]
     u = mw.log_mel_spectrogram(a[4321:204321], 80, padding=280000, device=dev)
     assert torch.equal(c, u)
+
+
+def test_unchunked_clamp_touches_only_the_tiles_that_need_it(dev):
+    """mw_logmel_long stores scaled values and revisits only tiles holding a value below max - 8: a clip with loud noise, a
+    digital-silence gap (every tile of it clamps) and a faint stretch (no tile clamps) must equal the oracle everywhere, and
+    calling again on a longer clip (the per-tile buffer grows) and on a shorter one must too."""
+    import manual_whisper_b200 as mw
+    from oracle.logmel import log_mel_spectrogram as oracle
+    rng = np.random.default_rng(9)
+    for secs in (40, 95, 12):
+        a = (0.1 * rng.standard_normal(16000 * secs)).astype(np.float32)
+        a[16000 * 5: 16000 * 8] = 0.0              # digital silence: -10 -> clamped to max - 8
+        a[16000 * 9: 16000 * 11] *= 1e-2           # 40 dB down: stays above the clamp
+        got = mw.log_mel_spectrogram(a, 128, device=dev).cpu()
+        ref = oracle(a, 128)
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() < TOL
+        lo = float(ref.max()) - 2.0
+        assert abs(float(got.min()) - lo) < TOL and float((got[:, 500:800] - lo).abs().max()) < TOL
