@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--beam", type=int, default=1, help="beam_size (BASELINE config 4: 5, patience 1, length_penalty 1)")
     ap.add_argument("--timestamps", action="store_true", help="without_timestamps=False: prompt [sot, lang, task], timestamp rules on")
     ap.add_argument("--language", default="zh")
+    ap.add_argument("--suffix", default="", help="appended to the fixture name (a second fixture of the same model, e.g. another audio seed)")
     args = ap.parse_args()
     from oracle.logmel import log_mel_spectrogram
     from oracle.model import OracleWhisper
@@ -95,7 +96,7 @@ def main():
             "audio_seed": args.audio_seed, "emb_std": args.emb_std, "prompt": prompt, "emu": "fp16", "beam": args.beam,
             "with_timestamps": bool(args.timestamps), "language": args.language,
             "generator": "scripts/make_parity_fixture.py", "seconds": time.time() - t0}
-    tag = (f"_beam{args.beam}" if args.beam > 1 else "") + ("_ts" if args.timestamps else "")
+    tag = (f"_beam{args.beam}" if args.beam > 1 else "") + ("_ts" if args.timestamps else "") + args.suffix
     path = fixture_path(args.model, args.scheme, tag)
     np.savez_compressed(path, ids_fp32=out["ids_fp32"], ids_emu=out["ids_emu"], margins=margins.astype(np.float16),
                         scores_fp32=scores["ids_fp32"], scores_emu=scores["ids_emu"],
