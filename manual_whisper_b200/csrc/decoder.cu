@@ -753,13 +753,17 @@ decode_attn_kernel(const mw_h* __restrict__ q, int ldq,
 // no score buffer; the 16 partial states of the CTA are merged at the end (log-sum-exp).  Same lane mapping as
 // decode_attn_kernel: 16 bytes per lane, 8 lanes per key, 4 keys per warp instruction.
 // ------------------------------------------------------------------------------------------------
+// UNR = independent K/V loads in flight per lane.  4 (95 registers, 5 CTAs/SM) is right when rows x heads fill the GPU (32
+// rows of large-v3 = 640 CTAs = one wave); when they do not (the 17-row shard of an 8-GPU job: 340 CTAs for 740 slots, 35 us
+// for bytes that need 21) UNR = 8 doubles the bytes in flight per CTA instead.  A group's keys are visited in the same order
+// either way, so the result is bit-identical and a sharded job decodes the ids of the single-GPU one.
+template <int UNR>
 __global__ void __launch_bounds__(128)
 cross_attn_stream_kernel(const mw_h* __restrict__ q, int ldq, const mw_h* __restrict__ kbase,
                          const mw_h* __restrict__ vbase, int64_t key_stride, int n_keys,
                          mw_h* __restrict__ out, int ldo, const char* pf, int pf_lines) {
     __shared__ float part_acc[16][64];
     __shared__ float part_m[16], part_l[16];
-    constexpr int UNR = 4;
     pdl_trigger();
     pdl_wait();
     const int h = blockIdx.x, r = blockIdx.y;
@@ -1601,12 +1605,19 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
                     attr[0].id = cudaLaunchAttributePriority;
                     attr[0].val.priority = s->prio_low;
                     cfg.attrs = attr; cfg.numAttrs = 1;
-                    MW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, cross_attn_stream_kernel, (const mw_h*)s->qx, d, (const mw_h*)kv,
+                    MW_CUDA_CHECK(cudaLaunchKernelEx(&cfg, cross_attn_stream_kernel<4>, (const mw_h*)s->qx, d, (const mw_h*)kv,
                                                      (const mw_h*)(kv + d), (int64_t)(2 * d), T, s->att, d, pf_xo, (int)(dd / 128)));
                     count_launch();
                 } else {
-                    launch_chained(cross_attn_stream_kernel, grid, dim3(128), 0, st, s->qx, d, kv, kv + d, 2 * d, T, s->att, d, pf_xo,
-                                   (int)(dd / 128));
+                    // under-filled grid (fewer CTAs than 3 per SM): more loads in flight per CTA, same arithmetic
+                    static const int unr_env = [] { const char* e = getenv("MW_XATTN_UNR"); return e ? atoi(e) : 0; }();   // A/B hook
+                    const bool deep = unr_env ? unr_env == 8 : (int)(grid.x * grid.y) <= 3 * device_sm_count();
+                    if (deep)
+                        launch_chained(cross_attn_stream_kernel<8>, grid, dim3(128), 0, st, s->qx, d, kv, kv + d, 2 * d, T, s->att, d, pf_xo,
+                                       (int)(dd / 128));
+                    else
+                        launch_chained(cross_attn_stream_kernel<4>, grid, dim3(128), 0, st, s->qx, d, kv, kv + d, 2 * d, T, s->att, d, pf_xo,
+                                       (int)(dd / 128));
                     MW_LAUNCH_CHECK();
                 }
             }
@@ -2067,7 +2078,7 @@ extern "C" mw_status mw_bench_kernel(mw_model* m, int which, int B, int iters, f
         if (which == 0) {
             mw_h* kv = s->kv_cross + (int64_t)l * c.max_batch * T * 2 * d;
             dim3 grid(c.n_heads, B);
-            cross_attn_stream_kernel<<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d, nullptr, 0);
+            cross_attn_stream_kernel<4><<<grid, 128, 0, st>>>(s->qx, d, kv, kv + d, 2 * d, T, s->att, d, nullptr, 0);
             MW_LAUNCH_CHECK();
             return MW_OK;
         }
