@@ -409,13 +409,14 @@ mw_status launch_ln_rows16(const float* x, const float* gamma, const float* beta
 
 // K = 5120-class shapes (16 warps): the same two-tile idea needs 160 weight registers, so K is walked in two halves of
 // KB blocks per warp (weights of one half in flight at a time) and the 16 warps reduce through 8 shared-memory slots.
-template <int KB, int NW>
+template <int KB, int NW, int WT>
 __global__ void __launch_bounds__(NW * 32, 1)
 skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h* __restrict__ W, int ldw,
                                 const float* __restrict__ bias, const float* resid, void* out, int ldo, int R, int N, int K,
                                 int flags, const char* pf, int pf_lines) {
     static_assert(NW == 16, "two rounds through 8 reduction slots");
-    constexpr int WT = 2;
+    // WT = 2 weight tiles per CTA; WT = 1 (a lone batch, mw_set_solo) doubles the CTAs and halves the bytes each waits for -
+    // per output element the K order and the reduction are the same, so both give the same bits
     __shared__ float red[NW / 2][32][WT * 16 + 1];
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -495,15 +496,22 @@ skinny_gemm_rows32_khalf_kernel(const mw_h* __restrict__ X, int ldx, const mw_h*
 
 template <int KB, int NW>
 mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
-                        int ldo, int R, int N, int K, int flags, cudaStream_t st, const char* pf, int pf_lines) {
+                        int ldo, int R, int N, int K, int flags, cudaStream_t st, const char* pf, int pf_lines, bool solo) {
     constexpr int WT = (NW <= 8 && KB <= 5) ? 2 : 1;          // two weight tiles where the registers allow it
     static const bool one_tile = [] { const char* e = getenv("MW_SKINNY_WT"); return e && e[0] == '1'; }();   // A/B hook
     if constexpr (NW == 16 && KB % 2 == 0 && KB / 2 <= 5) {
         static const bool no_khalf = [] { const char* e = getenv("MW_SKINNY_KHALF"); return e && e[0] == '0'; }();
         if (!one_tile && !no_khalf) {
-            dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
-            launch_chained(skinny_gemm_rows32_khalf_kernel<KB / 2, NW>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx, (const mw_h*)W,
-                           ldw, bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
+            static const int khalf_wt = [] { const char* e = getenv("MW_KHALF_WT"); return e ? atoi(e) : 0; }();   // A/B hook
+            if (khalf_wt == 1 || (khalf_wt == 0 && solo)) {       // a lone batch: 3.87 -> 3.76 ms per single-stream step
+                dim3 grid(ceil_div(N, 16), ceil_div(R, 32));
+                launch_chained(skinny_gemm_rows32_khalf_kernel<KB / 2, NW, 1>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx,
+                               (const mw_h*)W, ldw, bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
+            } else {
+                dim3 grid(ceil_div(N, 32), ceil_div(R, 32));
+                launch_chained(skinny_gemm_rows32_khalf_kernel<KB / 2, NW, 2>, grid, dim3(NW * 32), 0, st, (const mw_h*)X, ldx,
+                               (const mw_h*)W, ldw, bias, resid, out, ldo, R, N, K, flags, pf, pf_lines);
+            }
             MW_LAUNCH_CHECK();
             return MW_OK;
         }
@@ -524,7 +532,7 @@ mw_status launch_rows16(const void* X, int ldx, const void* W, int ldw, const fl
 // `next_w` / `next_bytes`: the weight matrix of the projection that follows this one in the step (prefetched into L2)
 mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const float* bias, const float* resid, void* out,
                       int ldo, int R, int N, int K, int flags, cudaStream_t st, bool allow_dg = true,
-                      const void* next_w = nullptr, int64_t next_bytes = 0) {
+                      const void* next_w = nullptr, int64_t next_bytes = 0, bool solo = false) {
     static const bool prefetch_on = [] { const char* e = getenv("MW_PREFETCH"); return !(e && e[0] == '0'); }();   // A/B hook
     const char* pf = prefetch_on ? (const char*)next_w : nullptr;
     const int pf_lines = pf ? (int)(next_bytes / 128) : 0;
@@ -535,7 +543,7 @@ mw_status skinny_gemm(const void* X, int ldx, const void* W, int ldw, const floa
     static const int dg_min_rows = [] { const char* e = getenv("MW_DG_MIN_ROWS"); return e ? atoi(e) : 96; }();
     if (allow_dg && R >= dg_min_rows && decode_gemm_supported(ldx, ldw, R, N, K))
         return decode_gemm_launch(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st);
-#define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st, pf, pf_lines)
+#define MW_SK(kb, nw) if (K == kb * nw * 32) return launch_rows16<kb, nw>(X, ldx, W, ldw, bias, resid, out, ldo, R, N, K, flags, st, pf, pf_lines, solo)
     MW_SK(5, 8);    // 1280  (large)
     MW_SK(10, 16);  // 5120  (large ffn)
     MW_SK(4, 8);    // 1024  (medium)
@@ -1630,7 +1638,7 @@ mw_status enqueue_layers(mw_model* m, int R, int beam, int idx_phase, cudaStream
             if (LN && (r = layernorm_launch(s->x, F(MW_DL_LN2_G), F(MW_DL_LN2_B), s->ln, R, d, st)) != MW_OK) return r;
             if (GM && (r = skinny_gemm(s->ln, d, W(MW_DL_W1), d, F(MW_DL_B1), nullptr, s->mlp, c.ffn, R, c.ffn, d, SK_FLAG_GELU, st, dg, W(MW_DL_W2), df)) != MW_OK) return r;
         }
-        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st, dg, next_qkv, 3 * dd)) != MW_OK) return r;
+        if (GM && (r = skinny_gemm(s->mlp, c.ffn, W(MW_DL_W2), c.ffn, F(MW_DL_B2), s->x, s->x, d, R, d, c.ffn, SK_FLAG_F32, st, dg, next_qkv, 3 * dd, s->solo)) != MW_OK) return r;
     }
     return MW_OK;
 }
