@@ -171,19 +171,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
         }
         const float mb = m_used * scale_log2e;
-        float ls0 = 0.0f, ls1 = 0.0f, ls2 = 0.0f, ls3 = 0.0f;
+        // exponent arguments and the four partial row sums as packed fp32 pairs (FFMA2 / FADD2: the same bits as the scalar
+        // form at half the issue slots - this kernel is bound by per-warp instruction latency, profiles/ncu_attention_r2.txt)
+        const uint64_t sc2 = pack2(scale_log2e, scale_log2e), nmb2 = pack2(-mb, -mb);
+        uint64_t ls01 = pack2(0.0f, 0.0f), ls23 = pack2(0.0f, 0.0f);
         uint32_t packed[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                const float p0 = ex2(fmaf(__uint_as_float(half ? r1[i] : r0[i]), scale_log2e, -mb));
-                const float p1 = ex2(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), scale_log2e, -mb));
-                if (i & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
+                float t0, t1;
+                unpack2(fma2(pack2(__uint_as_float(half ? r1[i] : r0[i]), __uint_as_float(half ? r1[i + 1] : r0[i + 1])), sc2, nmb2), t0, t1);
+                const float p0 = ex2(t0), p1 = ex2(t1);
+                if (i & 2) ls23 = add2(ls23, pack2(p0, p1)); else ls01 = add2(ls01, pack2(p0, p1));
                 mw_h2 hh = f2h2_bounded(p0, p1);      // p <= 2^8
                 packed[half * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
             }
         }
+        float ls0, ls1, ls2, ls3;
+        unpack2(ls01, ls0, ls1);
+        unpack2(ls23, ls2, ls3);
         l_run += (ls0 + ls1) + (ls2 + ls3);
         if (j > 0) {
             mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} has read sP and V buffer (j-1)&1 (long done by now)
@@ -193,11 +200,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             __syncwarp();
         }
-        unsigned char* prow = sP + tid * 128;
+        const uint32_t prow = smem_u32(sP) + tid * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const int chunk = g ^ (tid & 7);
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + chunk * 16), "r"(packed[4 * g]), "r"(packed[4 * g + 1]),
+                         "r"(packed[4 * g + 2]), "r"(packed[4 * g + 3]) : "memory");
         }
         fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
