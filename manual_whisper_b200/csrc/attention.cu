@@ -7,12 +7,16 @@
 //   softmax            thread reads its S row (64 fp32) with tcgen05.ld, max / exp2 in registers, writes the
 //                      un-normalised P (16-bit) into 128B-swizzled shared memory (A operand of the next MMA)
 //   O += P V_j         tcgen05.mma 128x64x64   (V_j: TMA tile [keys, d] used MN-major)      -> TMEM cols [64,128)
-// Round 2: O is ACCUMULATED IN TMEM across key blocks instead of being read back and rescaled in registers every block
-// (that was 2 tcgen05.ld + 64 FMAs per row per block on an issue-bound kernel).  The exponent reference of a row is only
-// moved - and its O row rescaled through tcgen05.ld/st - when a block's maximum exceeds it by more than 2^8 ("lazy
-// rescale": after the first blocks it practically never happens; P <= 256 fits 16-bit storage with the same relative
-// rounding), and S of block j+1 is issued as soon as every thread has copied S_j to registers, so it runs on the tensor
-// core under the softmax of block j.  K and V are double-buffered.  Three CTAs per SM (64 KB smem, 128 TMEM columns).
+// Round 2: O is ACCUMULATED IN TMEM across key blocks instead of being read back and rescaled in registers every block.  The
+// exponent reference of a row is only moved - and its O row rescaled through tcgen05.ld/st - when a block's maximum exceeds it
+// by more than 2^8 ("lazy rescale": after the first blocks it practically never happens; P <= 256 fits 16-bit storage with the
+// same relative rounding).
+// The kernel is bound by per-warp instruction latency (time ~ 1 / resident CTAs: 1843 / 1044 / 796 us at 1 / 2 / 3 CTAs per
+// SM; removing every exponential changes nothing - profiles/ncu_attention_r2.txt), so everything is arranged for FOUR CTAs per
+// SM, the most 128 TMEM columns each allow: one K and one V buffer (48 KB of shared memory; K_{j+1} is requested as soon as
+// S_j is complete, V_j as soon as P V_{j-1} is), P leaves for shared memory 8 columns at a time (124 registers, no spill), and
+// the exponent arguments and row sums run as packed fp32 pairs (FFMA2 / FADD2).  796 -> 588 us at the large-v3 shape
+// (627 TFLOP/s; cuDNN SDPA: 797), bit-identical output.
 #include "gemm.cuh"
 #include "ptx_sm100.cuh"
 
@@ -27,7 +31,7 @@ constexpr int DH = 64;
 constexpr int Q_BYTES = TQ * DH * 2;       // 16 KB
 constexpr int KV_BYTES = TK * DH * 2;      // 8 KB
 constexpr int P_BYTES = TQ * TK * 2;       // 16 KB: 128 rows x 128 bytes (one swizzle row per query)
-constexpr int ATT_SMEM = Q_BYTES + 4 * KV_BYTES + P_BYTES + 128 + 1024;   // K, V double-buffered; + barriers + alignment slack
+constexpr int ATT_SMEM = Q_BYTES + 2 * KV_BYTES + P_BYTES + 128 + 1024;   // one K and one V buffer; + barriers + alignment slack
 constexpr float RESCALE_LOG2 = 8.0f;       // a row's exponent reference moves only when a block maximum exceeds it by 2^8
 constexpr int ATT_TMEM_COLS = 128;         // S: cols [0,64)   O: cols [64,128)
 
@@ -37,23 +41,23 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                          mw_h* __restrict__ out, int Tq, int Tk_max, int colq0, int colk0, int colv0, int out_ld,
                          float scale_log2e, const int* __restrict__ kv_lens) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
-    unsigned char* sK = smem + Q_BYTES;                 // two K buffers
-    unsigned char* sV = sK + 2 * KV_BYTES;              // two V buffers
-    unsigned char* sP = sV + 2 * KV_BYTES;
+    unsigned char* sK = smem + Q_BYTES;                 // one K buffer
+    unsigned char* sV = sK + KV_BYTES;                  // one V buffer
+    unsigned char* sP = sV + KV_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* bar_q = bars;
-    uint64_t* bar_k = bars + 1;       // [2]
-    uint64_t* bar_v = bars + 3;       // [2]
-    uint64_t* bar_s = bars + 5;
-    uint64_t* bar_o = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* bar_k = bars + 1;
+    uint64_t* bar_v = bars + 2;
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_o = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * TQ;
@@ -68,7 +72,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (tid == 0) {
         prefetch_tensormap(&tmap_q);
         prefetch_tensormap(&tmap_kv);
-        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -88,10 +92,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     constexpr uint32_t idesc_o = make_idesc_h16(128, DH, 1);   // B (=V) is MN-major
 
     auto issue_s = [&](int j) {        // thread 0: S = Q K_j^T into TMEM cols [0,64)
-        mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
+        mbar_wait(bar_k, j & 1);
         tc_fence_after();
         const uint64_t dq = make_desc_sw128(smem_u32(sQ), 1024, 0);
-        const uint64_t dk = make_desc_sw128(smem_u32(sK + (j & 1) * KV_BYTES), 1024, 0);
+        const uint64_t dk = make_desc_sw128(smem_u32(sK), 1024, 0);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_h16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
         umma_commit(bar_s);
@@ -100,35 +104,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (tid == 0) {
         mbar_arrive_expect_tx(bar_q, Q_BYTES);
         tma_load_3d(sQ, &tmap_q, bar_q, col_q, q0, b);
-        for (int j = 0; j < 2 && j < n_blocks; ++j) {
-            mbar_arrive_expect_tx(&bar_k[j], KV_BYTES);
-            tma_load_3d(sK + j * KV_BYTES, &tmap_kv, &bar_k[j], col_k, j * TK, b);
-            mbar_arrive_expect_tx(&bar_v[j], KV_BYTES);
-            tma_load_3d(sV + j * KV_BYTES, &tmap_kv, &bar_v[j], col_v, j * TK, b);
-        }
+        mbar_arrive_expect_tx(bar_k, KV_BYTES);
+        tma_load_3d(sK, &tmap_kv, bar_k, col_k, 0, b);
+        mbar_arrive_expect_tx(bar_v, KV_BYTES);
+        tma_load_3d(sV, &tmap_kv, bar_v, col_v, 0, b);
         mbar_wait(bar_q, 0);
         issue_s(0);
     }
     __syncwarp();
 
     float m_used = -INFINITY, l_run = 0.0f;       // exponent reference of this row (raw score units), running sum of P
+    const uint32_t prow = smem_u32(sP) + tid * 128;
 
     for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(bar_s, j & 1);                  // S_j is in TMEM
+        mbar_wait(bar_s, j & 1);                  // S_j is in TMEM, so the K buffer is free
         tc_fence_after();
-        if (tid == 0 && j + 2 < n_blocks) {       // K buffer j&1 is free again
-            mbar_arrive_expect_tx(&bar_k[j & 1], KV_BYTES);
-            tma_load_3d(sK + (j & 1) * KV_BYTES, &tmap_kv, &bar_k[j & 1], col_k, (j + 2) * TK, b);
+        if (tid == 0 && j + 1 < n_blocks) {
+            mbar_arrive_expect_tx(bar_k, KV_BYTES);
+            tma_load_3d(sK, &tmap_kv, bar_k, col_k, (j + 1) * TK, b);
         }
         __syncwarp();
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_s + lane_off, r0);
         tmem_ld32(tmem_s + lane_off + 32, r1);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncthreads();                          // every thread holds its S_j row: the S columns may be overwritten
-        if (tid == 0 && j + 1 < n_blocks) issue_s(j + 1);      // runs on the tensor core under this block's softmax
-        __syncwarp();
 
         const int n_valid = min(TK, Tk - j * TK);    // >= 1
         if (n_valid < TK) {       // last, partial block only: masked keys contribute exp2(-inf) = 0
@@ -147,6 +146,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j > 0) {
+            mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} is done: O holds blocks 0..j-1, sP and the V buffer are free
+            tc_fence_after();
+            if (tid == 0) {
+                mbar_arrive_expect_tx(bar_v, KV_BYTES);
+                tma_load_3d(sV, &tmap_kv, bar_v, col_v, j * TK, b);
+            }
+            __syncwarp();
+        }
         // lazy rescale, decided per warp (tcgen05.ld/st are warp-wide): move the exponent reference only when some row of
         // the warp would otherwise produce P > 2^8
         const bool need = __any_sync(0xffffffffu, (mx - m_used) * scale_log2e > RESCALE_LOG2);
@@ -156,67 +164,56 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             l_run *= alpha;
             m_used = m_new;
             if (j > 0) {
-                mbar_wait(bar_o, (j - 1) & 1);    // O holds blocks 0..j-1
-                tc_fence_after();
-                uint32_t o0[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    tmem_ld32(tmem_o + lane_off + half * 32, o0);
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    uint32_t o0[8];
+                    tmem_ld8(tmem_o + lane_off + q8 * 8, o0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-                    tmem_st32(tmem_o + lane_off + half * 32, o0);
+                    for (int i = 0; i < 8; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+                    tmem_st8(tmem_o + lane_off + q8 * 8, o0);
                 }
                 tmem_st_wait();
             }
         }
         const float mb = m_used * scale_log2e;
         // exponent arguments and the four partial row sums as packed fp32 pairs (FFMA2 / FADD2: the same bits as the scalar
-        // form at half the issue slots - this kernel is bound by per-warp instruction latency, profiles/ncu_attention_r2.txt)
+        // form at half the issue slots - this kernel is bound by per-warp instruction latency, profiles/ncu_attention_r2.txt);
+        // P leaves for shared memory 8 columns at a time so that only four packed words are live
         const uint64_t sc2 = pack2(scale_log2e, scale_log2e), nmb2 = pack2(-mb, -mb);
         uint64_t ls01 = pack2(0.0f, 0.0f), ls23 = pack2(0.0f, 0.0f);
-        uint32_t packed[32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int g = 0; g < 8; ++g) {
+            uint32_t packed[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
+            for (int e = 0; e < 4; ++e) {
+                const int i = (g & 3) * 8 + 2 * e;
                 float t0, t1;
-                unpack2(fma2(pack2(__uint_as_float(half ? r1[i] : r0[i]), __uint_as_float(half ? r1[i + 1] : r0[i + 1])), sc2, nmb2), t0, t1);
+                unpack2(fma2(pack2(__uint_as_float(g < 4 ? r0[i] : r1[i]), __uint_as_float(g < 4 ? r0[i + 1] : r1[i + 1])), sc2, nmb2), t0, t1);
                 const float p0 = ex2(t0), p1 = ex2(t1);
                 if (i & 2) ls23 = add2(ls23, pack2(p0, p1)); else ls01 = add2(ls01, pack2(p0, p1));
                 mw_h2 hh = f2h2_bounded(p0, p1);      // p <= 2^8
-                packed[half * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
+                packed[e] = *reinterpret_cast<uint32_t*>(&hh);
             }
+            const int chunk = g ^ (tid & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + chunk * 16), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]),
+                         "r"(packed[3]) : "memory");
         }
         float ls0, ls1, ls2, ls3;
         unpack2(ls01, ls0, ls1);
         unpack2(ls23, ls2, ls3);
         l_run += (ls0 + ls1) + (ls2 + ls3);
-        if (j > 0) {
-            mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} has read sP and V buffer (j-1)&1 (long done by now)
-            if (tid == 0 && j + 1 < n_blocks) {
-                mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], KV_BYTES);
-                tma_load_3d(sV + ((j + 1) & 1) * KV_BYTES, &tmap_kv, &bar_v[(j + 1) & 1], col_v, (j + 1) * TK, b);
-            }
-            __syncwarp();
-        }
-        const uint32_t prow = smem_u32(sP) + tid * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int chunk = g ^ (tid & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + chunk * 16), "r"(packed[4 * g]), "r"(packed[4 * g + 1]),
-                         "r"(packed[4 * g + 2]), "r"(packed[4 * g + 3]) : "memory");
-        }
         fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
-        __syncthreads();          // P complete, rescaled O rows stored
+        __syncthreads();          // P complete, rescaled O rows stored, every thread holds its S_j row
         if (tid == 0) {
-            mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
+            if (j + 1 < n_blocks) issue_s(j + 1);
+            mbar_wait(bar_v, j & 1);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TK / 16; ++k) {
                 const uint64_t dp = make_desc_sw128(smem_u32(sP) + k * 32, 1024, 0);
-                const uint64_t dv = make_desc_sw128(smem_u32(sV + (j & 1) * KV_BYTES) + k * 2048, 1024, KV_BYTES);
+                const uint64_t dv = make_desc_sw128(smem_u32(sV) + k * 2048, 1024, KV_BYTES);
                 umma_h16(tmem_o, dp, dv, idesc_o, (j | k) ? 1u : 0u);
             }
             umma_commit(bar_o);
