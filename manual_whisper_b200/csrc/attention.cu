@@ -128,6 +128,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tmem_ld32(tmem_s + lane_off, r0);
         tmem_ld32(tmem_s + lane_off + 32, r1);
         tmem_ld_wait();
+        if (j > 0) {
+            mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} is done: O holds blocks 0..j-1, sP and the V buffer are free
+            tc_fence_after();
+            if (tid == 0) {
+                mbar_arrive_expect_tx(bar_v, KV_BYTES);
+                tma_load_3d(sV, &tmap_kv, bar_v, col_v, j * TK, b);
+            }
+            __syncwarp();
+        }
 
         const int n_valid = min(TK, Tk - j * TK);    // >= 1
         if (n_valid < TK) {       // last, partial block only: masked keys contribute exp2(-inf) = 0
@@ -146,15 +155,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (j > 0) {
-            mbar_wait(bar_o, (j - 1) & 1);        // P V_{j-1} is done: O holds blocks 0..j-1, sP and the V buffer are free
-            tc_fence_after();
-            if (tid == 0) {
-                mbar_arrive_expect_tx(bar_v, KV_BYTES);
-                tma_load_3d(sV, &tmap_kv, bar_v, col_v, j * TK, b);
-            }
-            __syncwarp();
-        }
         // lazy rescale, decided per warp (tcgen05.ld/st are warp-wide): move the exponent reference only when some row of
         // the warp would otherwise produce P > 2^8
         const bool need = __any_sync(0xffffffffu, (mx - m_used) * scale_log2e > RESCALE_LOG2);
