@@ -123,4 +123,4 @@ def test_unchunked_clamp_touches_only_the_tiles_that_need_it(dev):
         assert got.shape == ref.shape
         assert (got - ref).abs().max().item() < TOL
         lo = float(ref.max()) - 2.0
-        assert abs(float(got.min()) - lo) < TOL and float((got[:, 500:800] - lo).abs().max()) < TOL
+        assert abs(float(got.min()) - lo) < TOL and float((got[:, 503:797] - lo).abs().max()) < TOL    # frames wholly inside the gap
