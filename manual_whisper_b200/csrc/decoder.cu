@@ -301,7 +301,7 @@ skinny_gemm_ln_kernel(const float* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int rl = rl0 + h * NW;
-            if (rl >= 32) break;
+            if (rl >= 32 || r0 + rl >= R) break;      // rows past the batch: their products are never stored (warp-uniform)
             float s = 0.0f;
 #pragma unroll
             for (int i = 0; i < MAXV; ++i) s += (v[h][i].x + v[h][i].y) + (v[h][i].z + v[h][i].w);
