@@ -1081,7 +1081,7 @@ constexpr int SEL_THREADS = 512;
 // including the "timestamp mass beats every text token" rule, and returns max/argmax + logsumexp.
 __device__ void row_rules_and_stats(float* lg, int V, const RowRule& rr, const GenOptsDev& o, const uint8_t* sup,
                                     const uint8_t* beg, ValIdx& best_out, float& lse_out) {
-    __shared__ ValIdx s_all[SEL_THREADS / 32], s_txt[SEL_THREADS / 32], s_ts[SEL_THREADS / 32];
+    __shared__ ValIdx s_txt[SEL_THREADS / 32], s_ts[SEL_THREADS / 32];
     __shared__ float s_sum[2][SEL_THREADS / 32];
     __shared__ ValIdx b_all, b_txt, b_ts;
     __shared__ float f_sum_all, f_sum_ts;
