@@ -30,18 +30,18 @@ def _report(tag, cmp):
           f"{[(d['window'], d['step'], round(d['oracle_margin'], 4)) for d in cmp['divergences']]}")
 
 
-@pytest.mark.parametrize("model", ["tiny", "small"])
-def test_128_windows_identical_to_both_oracles(model):
+@pytest.mark.parametrize("model,tag", [("tiny", ""), ("tiny", "_seed3"), ("small", "")])
+def test_128_windows_identical_to_both_oracles(model, tag):
     from scripts.gpu_parity_stats import engine_ids, compare
-    fx, meta = _fixture(model)
+    fx, meta = _fixture(model, tag)
     n = meta["windows"]
     assert n >= 64
     got, offs, lens, _ = engine_ids(meta, n)
     assert np.array_equal(offs, fx["offs"]) and np.array_equal(lens, fx["lens"])          # same windows as the oracle decoded
     margins = fx["margins"].astype(np.float32)
     # the inputs are not a degenerate constant: ids differ between windows and change inside a window (at d = 768 the scheme is
-    # far more repetitive than at d = 384: 16 distinct sequences among 128 windows against 71)
-    assert len({tuple(r) for r in fx["ids_fp32"].tolist()}) >= (n // 2 if model == "tiny" else 8)
+    # far more repetitive than at d = 384: 16 distinct sequences among 128 windows against 59-71)
+    assert len({tuple(r) for r in fx["ids_fp32"].tolist()}) >= (n // 3 if model == "tiny" else 8)
     for tag, ref in ((f"{model} vs rounding oracle", fx["ids_emu"]), (f"{model} vs fp32 oracle", fx["ids_fp32"])):
         cmp = compare(got, ref, margins)
         _report(tag, cmp)
